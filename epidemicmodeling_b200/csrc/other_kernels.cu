@@ -1,0 +1,290 @@
+// other_kernels.cu -- SEIRP ensembles, SI-alpha rollout fused with NPICost,
+// SI rollout, Pareto front + knee, knee-schedule gather (sm_100a, FP64,
+// --fmad=false).  One thread per trajectory; every per-step store of a warp is
+// a single coalesced 256-byte transaction (trajectory-minor layout).
+#include "epi_internal.h"
+#include "epi_device.cuh"
+
+namespace epi {
+
+// ===========================================================================
+// SEIRP / SEIRPSaturatedResource   (Tools/SEIRP.m:13-32,
+//                                   Tools/SEIRPSaturatedResource.m:13-36)
+// ===========================================================================
+template <int RATE_MODE, bool SAT, bool FULL>
+__global__ void __launch_bounds__(256) seirp_kernel(const __grid_constant__ SeirpParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const size_t B = (size_t)P.B;
+  const int K = P.K;
+  const double dt = P.dt;
+  double S = P.ic[0 * B + b], E = P.ic[1 * B + b], I = P.ic[2 * B + b], R = P.ic[3 * B + b],
+         Pd = P.ic[4 * B + b];
+  double ae = 0, ai = 0, ka = 0, ro = 0, be = 0, mu = 0, ga = 0;
+  if (RATE_MODE == EPI_RATES_CONST) {
+    ae = P.rates[0 * B + b]; ai = P.rates[1 * B + b]; ka = P.rates[2 * B + b];
+    ro = P.rates[3 * B + b]; be = P.rates[4 * B + b]; mu = P.rates[5 * B + b];
+    ga = P.rates[6 * B + b];
+  }
+  double *__restrict__ out = P.out;
+  const size_t KB = (size_t)K * B;
+  if (K <= 0) return;
+  if (FULL) {
+    out[0 * KB + b] = S; out[1 * KB + b] = E; out[2 * KB + b] = I; out[3 * KB + b] = R;
+    out[4 * KB + b] = Pd;  // :20-24
+  }
+  for (int t = 0; t + 1 < K; ++t) {  // :26  (only rate samples 0..K-2 are read)
+    if (RATE_MODE == EPI_RATES_SHARED_SERIES) {
+      const double *r = P.rates + t;
+      ae = r[0]; ai = r[(size_t)K]; ka = r[(size_t)2 * K]; ro = r[(size_t)3 * K];
+      be = r[(size_t)4 * K]; mu = r[(size_t)5 * K]; ga = r[(size_t)6 * K];
+    } else if (RATE_MODE == EPI_RATES_SERIES) {
+      const double *r = P.rates + (size_t)t * 7 * B + b;
+      ae = r[0]; ai = r[B]; ka = r[2 * B]; ro = r[3 * B]; be = r[4 * B]; mu = r[5 * B]; ga = r[6 * B];
+    }
+    if (SAT) {
+      const double h = (tanh((I - P.i_0) / P.sigma) + 1.0) / 2.0;  // Saturated :27
+      be = (P.beta_s - P.beta_0) * h + P.beta_0;                    // :28
+      mu = (P.mu_s - P.mu_0) * h + P.mu_0;                          // :29
+    }
+    // :27-31 as MATLAB parses them (unary minus first, then left to right)
+    const double Sn = ((((-ae) * S) * E - (ai * S) * I) + ga * R) * dt + S;
+    const double En = (((((ae * S) * E) + ((ai * S) * I)) - ka * E) - ro * E) * dt + E;
+    const double In = ((ka * E - be * I) - mu * I) * dt + I;
+    const double Rn = ((be * I + ro * E) - ga * R) * dt + R;
+    const double Pn = (mu * I) * dt + Pd;
+    S = Sn; E = En; I = In; R = Rn; Pd = Pn;
+    if (FULL) {
+      const size_t o = (size_t)(t + 1) * B + b;
+      out[0 * KB + o] = S; out[1 * KB + o] = E; out[2 * KB + o] = I; out[3 * KB + o] = R;
+      out[4 * KB + o] = Pd;
+    }
+  }
+  if (!FULL) {
+    out[0 * B + b] = S; out[1 * B + b] = E; out[2 * B + b] = I; out[3 * B + b] = R;
+    out[4 * B + b] = Pd;
+  }
+}
+
+template <int RM, bool SAT>
+static void seirp_launch2(const SeirpParams &p, cudaStream_t st, int grid, int block) {
+  if (p.out_mode == EPI_SEIRP_OUT_FULL) seirp_kernel<RM, SAT, true><<<grid, block, 0, st>>>(p);
+  else seirp_kernel<RM, SAT, false><<<grid, block, 0, st>>>(p);
+}
+template <int RM>
+static void seirp_launch1(const SeirpParams &p, cudaStream_t st, int grid, int block) {
+  if (p.saturated) seirp_launch2<RM, true>(p, st, grid, block);
+  else seirp_launch2<RM, false>(p, st, grid, block);
+}
+void launch_seirp(const SeirpParams &p, cudaStream_t st) {
+  const int block = 128;
+  const int grid = (p.B + block - 1) / block;
+  if (p.rate_mode == EPI_RATES_CONST) seirp_launch1<EPI_RATES_CONST>(p, st, grid, block);
+  else if (p.rate_mode == EPI_RATES_SHARED_SERIES) seirp_launch1<EPI_RATES_SHARED_SERIES>(p, st, grid, block);
+  else seirp_launch1<EPI_RATES_SERIES>(p, st, grid, block);
+}
+
+// ===========================================================================
+// SIalpha_Controlled (Tools/SIalpha_Controlled.m:15-32) fused with NPICost
+// (Tools/NPICost.m:6-10) as chained in TrainPredictPrescribeNPI.m:481-493,512-519
+// ===========================================================================
+// U_KIND: EPI_U_F64, EPI_U_U8, 2 = per-day scalars precomputed by eks_backward
+template <int U_KIND>
+__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const size_t B = (size_t)P.B;
+  const int g = b / P.G;
+  const epi_model_params *__restrict__ prm = P.prm + g;
+  const int K = P.K, L = P.L;
+  const double dt = prm->dt, beta = prm->beta, gamma = prm->gamma, bb = prm->b;
+  const double amin = prm->alpha_min, amax = prm->alpha_max;
+  double S = P.x0[3 * g + 0], I = P.x0[3 * g + 1], A = P.x0[3 * g + 2];
+  double sd_s = 0.0, sd_i = 0.0, sd_a = 0.0;
+  if (P.noise_std) { sd_s = P.noise_std[3 * g + 0]; sd_i = P.noise_std[3 * g + 1]; sd_a = P.noise_std[3 * g + 2]; }
+  const bool want_cost = P.J0 != nullptr;
+  // NPICost accumulators continue the per-group history prefixes
+  double a0 = 0.0, a1 = 0.0;
+  if (want_cost) {
+    if (U_KIND == 2) {
+      const double *nh = P.newcases_hist + (size_t)g * P.T_hist;
+      for (int t = 0; t < P.T_hist; ++t) a0 += nh[t];
+      for (int t = 0; t < P.T_hist; ++t) a1 += P.cost_day[(size_t)t * B + b];
+    } else {
+      a0 = P.j0_prefix ? P.j0_prefix[g] : 0.0;
+      a1 = P.j1_prefix ? P.j1_prefix[g] : 0.0;
+    }
+  }
+  const int Th = (U_KIND == 2) ? P.T_hist : 0;
+  for (int t = 0; t < K; ++t) {  // :24-28
+    double dot, cday = 0.0;
+    if (U_KIND == 2) {
+      dot = P.dot_day[(size_t)(Th + t) * B + b];
+      cday = P.cost_day[(size_t)(Th + t) * B + b];
+    } else {
+      dot = 0.0;
+      const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
+#pragma unroll
+      for (int j = 0; j < EPI_LMAX; ++j) {
+        if (j < L) {
+          double uj;
+          if (U_KIND == EPI_U_F64) uj = ((const double *)P.u)[((size_t)t * L + j) * B + b];
+          else uj = (double)((const unsigned char *)P.u)[((size_t)t * L + j) * B + b];
+          const double gj = gamma * prm->a[j];
+          const double d = prm->u_max[j] - uj;
+          dot = (j == 0) ? gj * d : fma(gj, d, dot);
+          if (wd) {
+            const double wu = wd[j] * uj;
+            cday = (j == 0) ? wu : (cday + wu);
+          }
+        }
+      }
+    }
+    double ns = 0.0, ni = 0.0, na = 0.0;
+    if (P.noise) {
+      ns = P.noise[((size_t)t * 3 + 0) * B + b];
+      ni = P.noise[((size_t)t * 3 + 1) * B + b];
+      na = P.noise[((size_t)t * 3 + 2) * B + b];
+    }
+    const double asi = (A * S) * I;
+    const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + ns * sd_s)));
+    const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + ni * sd_i)));
+    const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dot) + na * sd_a)));
+    S = Sn; I = In; A = An;
+    if (P.s) P.s[(size_t)t * B + b] = S;
+    if (P.i) P.i[(size_t)t * B + b] = I;
+    if (P.alpha) P.alpha[(size_t)t * B + b] = A;
+    if (want_cost) {
+      a0 += (S * I) * A;  // s.*i.*alpha (:493)
+      a1 += cday;
+    }
+  }
+  if (want_cost) {
+    P.J0[b] = a0 / (double)P.T_total;                        // NPICost.m:6
+    P.J1[b] = a1 / (double)((size_t)L * (size_t)P.T_total);  // NPICost.m:10
+  }
+}
+
+void launch_rollout(const RolloutParams &p, cudaStream_t st) {
+  const int block = 128;
+  const int grid = (p.B + block - 1) / block;
+  if (p.u_kind == EPI_U_F64) rollout_kernel<EPI_U_F64><<<grid, block, 0, st>>>(p);
+  else if (p.u_kind == EPI_U_U8) rollout_kernel<EPI_U_U8><<<grid, block, 0, st>>>(p);
+  else rollout_kernel<2><<<grid, block, 0, st>>>(p);
+}
+
+// ===========================================================================
+// SI_Controlled (Tools/SI_Controlled.m:12-22)
+// ===========================================================================
+__global__ void __launch_bounds__(256) si_kernel(const __grid_constant__ SiParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const size_t B = (size_t)P.B;
+  if (P.K <= 0) return;
+  const double dt = P.dt, beta = P.beta[b];
+  double S = P.s0[b], I = P.i0[b];
+  P.s[b] = S; P.i[b] = I;  // :15-16
+  for (int t = 0; t + 1 < P.K; ++t) {  // :19-22
+    const double A = P.alpha[(size_t)t * B + b];
+    const double Sn = mmax(0.0, mmin(1.0, S - ((dt * A) * S) * I));
+    const double In = mmax(0.0, mmin(1.0, I + dt * (((A * S) * I) - beta * I)));
+    S = Sn; I = In;
+    P.s[(size_t)(t + 1) * B + b] = S;
+    P.i[(size_t)(t + 1) * B + b] = I;
+  }
+}
+void launch_si(const SiParams &p, cudaStream_t st) {
+  const int block = 128;
+  si_kernel<<<(p.B + block - 1) / block, block, 0, st>>>(p);
+}
+
+// ===========================================================================
+// Pareto front + knee (Tools/TrainPredictPrescribeNPI.m:624-633)
+// one CTA per point set; points staged in shared memory; the dominance count of
+// the reference (strict in both coordinates, ties survive) is evaluated as-is,
+// the max / arg-min reductions use warp shuffles.
+// ===========================================================================
+constexpr int kParetoBlock = 256;
+__global__ void __launch_bounds__(kParetoBlock) pareto_kernel(const __grid_constant__ ParetoParams P) {
+  extern __shared__ double sm[];  // [2][n]
+  const int n = P.n;
+  const int set = blockIdx.x;
+  double *s0 = sm, *s1 = sm + n;
+  const double *J0 = P.J0 + (size_t)set * n, *J1 = P.J1 + (size_t)set * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { s0[i] = J0[i]; s1[i] = J1[i]; }
+  __syncthreads();
+  // maxima (MATLAB max skips NaN)
+  double m0 = __longlong_as_double(0x7ff8000000000000ll), m1 = m0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { m0 = mmax(m0, s0[i]); m1 = mmax(m1, s1[i]); }
+  __shared__ double red0[kParetoBlock / 32], red1[kParetoBlock / 32];
+  __shared__ int redi[kParetoBlock / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m0 = mmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+    m1 = mmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red0[wid] = m0; red1[wid] = m1; }
+  __syncthreads();
+  m0 = red0[0]; m1 = red1[0];
+#pragma unroll
+  for (int w = 1; w < kParetoBlock / 32; ++w) { m0 = mmax(m0, red0[w]); m1 = mmax(m1, red1[w]); }
+  __syncthreads();
+  // dominance filter + knee candidate
+  double bv = __longlong_as_double(0x7ff8000000000000ll);
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double x0 = s0[i], x1 = s1[i];
+    if (P.on_front) {
+      int cnt = 0;
+      for (int j = 0; j < n; ++j) cnt += (s0[j] < x0) && (s1[j] < x1);
+      P.on_front[(size_t)set * n + i] = (cnt == 0) ? 1 : 0;
+    }
+    const double q0 = x0 / m0, q1 = x1 / m1;
+    const double v = q0 * q0 + q1 * q1;
+    if (v == v && (bv != bv || v < bv)) { bv = v; bi = i; }  // first minimum, NaN skipped
+  }
+  if (P.I_opt) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const bool take = (ov == ov) && (bv != bv || ov < bv || (ov == bv && oi < bi));
+      if (take) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red0[wid] = bv; redi[wid] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < kParetoBlock / 32; ++w) {
+        const double ov = red0[w];
+        const int oi = redi[w];
+        const bool take = (ov == ov) && (bv != bv || ov < bv || (ov == bv && oi < bi));
+        if (take) { bv = ov; bi = oi; }
+      }
+      P.I_opt[set] = (bi == 0x7fffffff) ? 0 : bi;
+    }
+  }
+}
+void launch_pareto(const ParetoParams &p, cudaStream_t st) {
+  const size_t smem = (size_t)2 * p.n * sizeof(double);
+  cudaFuncSetAttribute(pareto_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  pareto_kernel<<<p.n_sets, kParetoBlock, smem, st>>>(p);
+}
+
+__global__ void gather_knee_kernel(const double *__restrict__ u_fore, const int *__restrict__ I_opt,
+                                   double *__restrict__ u_knee, int n_regions, int n_eps, int TfL) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)n_regions * TfL) return;
+  const int r = (int)(q / TfL), f = (int)(q % TfL);
+  const size_t B = (size_t)n_regions * n_eps;
+  u_knee[q] = u_fore[(size_t)f * B + (size_t)r * n_eps + I_opt[r]];
+}
+void launch_gather_knee(const double *u_fore, const int *I_opt, double *u_knee, int n_regions,
+                        int n_eps, int Tf, int L, cudaStream_t st) {
+  const size_t total = (size_t)n_regions * Tf * L;
+  if (!total) return;
+  gather_knee_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(u_fore, I_opt, u_knee,
+                                                                     n_regions, n_eps, Tf * L);
+}
+
+}  // namespace epi

@@ -127,8 +127,15 @@ void orc_npicost(const double *newcases, int T, const double *inputs, const doub
   double a0 = 0.0;
   for (int t = 0; t < T; ++t) a0 += newcases[t];
   *J0 = a0 / (double)T; /* NPICost.m:6 */
+  /* NPICost.m:9-10: mean(weighted_inputs(:)).  MATLAB's sum order is
+   * unspecified; DEFINED here as column (= day) sums in row order, then the
+   * day sums in day order. */
   double a1 = 0.0;
-  for (size_t k = 0; k < (size_t)L * T; ++k) a1 += weights[k] * inputs[k]; /* :9-10 */
+  for (int t = 0; t < T; ++t) {
+    double c = weights[(size_t)t * L] * inputs[(size_t)t * L];
+    for (int j = 1; j < L; ++j) c = c + weights[(size_t)t * L + j] * inputs[(size_t)t * L + j];
+    a1 += c;
+  }
   *J1 = a1 / (double)((size_t)L * T);
 }
 

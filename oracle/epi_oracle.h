@@ -95,7 +95,7 @@ void orc_si_controlled(const double *alpha, double beta, double s0, double i0, i
                        double *s, double *i);
 
 /* Tools/NPICost.m:6-10.  inputs/weights are LxT column-major; sums run in
- * linear (column-major) index order. */
+ * a defined order: per-day column sums (row order), then over days. */
 void orc_npicost(const double *newcases, int T, const double *inputs, const double *weights,
                  int L, double *J0, double *J1);
 
