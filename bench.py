@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- the optimal-NPI Pareto sweep (BASELINE.json config 4, the configuration
+the headline metric "EKF/EKS+optimal-NPI trajectory-days/sec" is quoted on).
+
+One "step" = one pass of the hot path over one batch: for every (region, epsilon) the
+6-state EKF + fixed-interval smoother over T = T_hist + T_fore days, the SIalpha rollout
+of the smoothed schedule, NPICost, then the per-region Pareto front + knee, and (N > 1)
+the path's single collective: an all-gather of the per-shard (J0, J1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+  value : trajectory-days/s, whole job, inputs resident in HBM (device-memory C-ABI mode)
+  e2e   : the same through the blocking host-memory C-ABI call (pinned host buffers,
+          H2D + D2H inside the timed region) -- the call a MATLAB/Octave host makes
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+Multi-GPU: one process per GPU (torchrun), weak scaling: every rank runs a full
+236-region replica (different synthetic seeds), no data-path collective except the gather.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# canonical work per trajectory-day (DESIGN.md "Measurement")
+FLOPS_EKF_EKS_M6 = 4758.0
+BYTES_FUSED_M6 = 864.0            # packed tape written once + read once
+KERNEL_ALGO = {                   # per trajectory-day: (algorithmic bytes, canonical flops)
+    "ekf_forward": (432.0, 2314.0),   # tape write (S-, S+, packed P-, P+)
+    "eks_gain": (432.0, 1310.0),      # tape read; P+A' + pinv + product + Jacobian
+    "eks_backward": (0.0, 204.0),     # S_SMOOTH recursion + schedule; P_SMOOTH is not needed for (J0, J1)
+    "rollout_cost": (0.0, 91.0),
+    "pareto": (0.0, 0.0),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regions", type=int, default=236)
+    ap.add_argument("--eps", type=int, default=250)
+    ap.add_argument("--t-hist", type=int, default=441)
+    ap.add_argument("--t-fore", type=int, default=120)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"optimal-NPI Pareto sweep (testPrescribeXPRIZE02 shape): {a.regions} regions x {a.eps} eps x "
+            f"12 NPIs x ({a.t_hist}+{a.t_fore}) days")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def build_inputs(a, rank):
+    from epidemicmodeling_b200 import synthetic as syn
+    # weak scaling: every rank gets its own 236-region replica (different seeds)
+    inp = syn.sweep_inputs(n_regions=a.regions, T_hist=a.t_hist, T_fore=a.t_fore, seed_u=2 + 100003 * rank,
+                           seed_x=3 + 100003 * rank)
+    eps = syn.epsilon_grid_xprize02(a.eps)
+    return inp, eps
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def oracle_regions(inp, S_fixed):
+    """OrcSweepRegion objects from the inputs and a [T,3,nR] fixed-input smoother result."""
+    from oracle import oracle as orc
+    regs = []
+    for r, rin in enumerate(inp):
+        s6, Th = rin["setup6"], rin["T_hist"]
+        Sr = S_fixed[:, :, r].T
+        regs.append(orc.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                                    s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], s6["beta_ekf"],
+                                    s6["gamma_ekf"], s6["W"], Sr[0, Th - 1], Sr[1, Th - 1], Sr[2, Th - 1],
+                                    (Sr[0, :Th] * Sr[1, :Th]) * Sr[2, :Th], rin["weights"]))
+    return regs
+
+
+def oracle_fixed_input(inp):
+    from oracle import oracle as orc
+    out = []
+    for rin in inp:
+        s3 = rin["setup3"]
+        o3 = orc.ekf_eks(orc.SIALPHA, rin["u_fixed"], rin["x"], s3["params"], s3["s_init"], s3["Ps_init"],
+                         s3["s_final"], s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], rin["R_v"], s3["beta_ekf"],
+                         s3["gamma_ekf"], s3["W"], 1)
+        out.append(o3["S_SMOOTH"].T)
+    return np.stack(out, axis=2)  # [T,3,nR]
+
+
+def cpu_sample(a, inp, eps, seconds):
+    """Time the CPU oracle (all host threads, OpenMP over trajectories) on a bounded sample
+    of the same workload: the first n regions x all epsilon.  Returns (value, cores, sample, n)."""
+    from oracle import oracle as orc
+    T = a.t_hist + a.t_fore
+    cores = orc.num_threads()
+    probe = inp[:1]
+    regs = oracle_regions(probe, oracle_fixed_input(probe))
+    t0 = time.perf_counter()
+    orc.sweep_batch(regs, eps, n_threads=cores)
+    t1 = time.perf_counter() - t0
+    n = int(max(1, min(len(inp), round(seconds / max(t1, 1e-6)))))
+    return n, cores, t1
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path.  Octave/MATLAB do not
+    exist in this image, so this is the C oracle (a line-by-line port of the .m files) with all
+    host threads -- kind "port".  Each step = a bounded sample (n regions x all epsilon)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+    inp, eps = build_inputs(a, 0)
+    T = a.t_hist + a.t_fore
+    budget = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
+    n, cores, _ = cpu_sample(a, inp, eps, budget)
+    sample = inp[:n]
+    regs = oracle_regions(sample, oracle_fixed_input(sample))
+    for _ in range(a.warmup):
+        orc.sweep_batch(regs, eps, n_threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        orc.sweep_batch(regs, eps, n_threads=cores)
+    dt = (time.perf_counter() - t0) / max(1, a.steps)
+    units = n * a.eps * T
+    val = units / dt
+    sample_s = f"{n} of {a.regions} regions x {a.eps} eps x {T} days per step (OpenMP over trajectories)"
+    line = {"impl": "reference", "metric": "trajectory_days_per_sec", "value": val, "unit": "trajectory-days/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "note": "CPU oracle port of the reference .m files; "
+                       "Octave/MATLAB absent from the image"},
+            "cpu_baseline": {"value": val, "unit": "trajectory-days/s", "cores": cores, "kind": "port",
+                             "sample": sample_s},
+            "e2e": {"value": val, "unit": "trajectory-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from epidemicmodeling_b200 import workloads as wl
+    from epidemicmodeling_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    T = a.t_hist + a.t_fore
+    inp, eps = build_inputs(a, rank)
+    eng = Engine(local)
+    eng.use_torch_stream()
+
+    # driver glue before the sweep (TrainPredictPrescribeNPI.m:377-392): fixed-input 3-state EKF/EKS
+    S_fixed = wl.run_fixed_input(eng, inp)
+    batch = wl.sweep_batch(inp, S_fixed)
+    dbatch = wl.sweep_to_device(batch, eps, dev)
+    nR, nE = a.regions, a.eps
+    out = {"J0": torch.empty((nR, nE), dtype=torch.float64, device=dev),
+           "J1": torch.empty((nR, nE), dtype=torch.float64, device=dev),
+           "on_front": torch.empty((nR, nE), dtype=torch.uint8, device=dev),
+           "I_opt": torch.empty((nR,), dtype=torch.int32, device=dev)}
+    gathered = torch.empty((world, 2, nR, nE), dtype=torch.float64, device=dev) if world > 1 else None
+    send = torch.empty((2, nR, nE), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        wl.run_sweep(eng, dbatch, None, out=out)
+        if world > 1:  # the one collective: all-gather of per-shard costs over NVLink
+            send[0].copy_(out["J0"]); send[1].copy_(out["J1"])
+            dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        step()
+    fence()
+    launches0 = eng.launch_count
+    ktimes = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    ev0.record()
+    for _ in range(a.steps):
+        step()
+        # per-kernel CUDA-event durations recorded by the library on the launching stream
+        # (read back lazily after the region: the events are only queried here)
+    ev1.record()
+    fence()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.launch_count - launches0
+    # per-kernel durations: one extra (untimed) step so the event queries do not perturb the timed region
+    per_kernel_runs = []
+    for _ in range(3):
+        step()
+        torch.cuda.synchronize()
+        per_kernel_runs.append(eng.last_kernel_times())
+    for k in per_kernel_runs[0]:
+        ktimes[k] = float(np.mean([r[k] for r in per_kernel_runs]))
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    units_rank = nR * nE * T
+    value = units_rank * world / (ms_step * 1e-3)
+
+    # ---- e2e: the blocking host-memory C-ABI call with pinned host buffers
+    e2e = None
+    if not a.no_e2e:
+        pinned = {}
+        h2d = 0
+        for k in wl._SWEEP_ARRAYS:
+            tt = torch.from_numpy(np.ascontiguousarray(batch[k])).pin_memory()
+            pinned[k] = tt.numpy()
+            h2d += tt.numel() * 8
+        hb = dict(batch)
+        hb.update(pinned)
+        peps = torch.from_numpy(np.ascontiguousarray(eps)).pin_memory().numpy()
+        h2d += peps.size * 8 + len(bytes(memoryview(batch["prm"])))
+        hout = {"J0": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
+                "J1": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
+                "on_front": torch.empty((nR, nE), dtype=torch.uint8).pin_memory().numpy(),
+                "I_opt": torch.empty((nR,), dtype=torch.int32).pin_memory().numpy()}
+        d2h = sum(v.nbytes for v in hout.values())
+
+        def step_host():
+            wl.run_sweep(eng, hb, peps, out=hout)   # blocking: H2D, kernels, D2H, stream sync
+            if world > 1:
+                send[0].copy_(torch.from_numpy(hout["J0"]), non_blocking=True)
+                send[1].copy_(torch.from_numpy(hout["J1"]), non_blocking=True)
+                dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
+
+        for _ in range(2):
+            step_host()
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step_host()
+        e1.record()
+        fence()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item()) / a.steps
+        e2e = {"value": units_rank * world / (ms_e2e * 1e-3), "unit": "trajectory-days/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e}
+        # parity of the two legs: same bits from the host-memory and device-memory modes
+        assert np.array_equal(hout["J0"], out["J0"].cpu().numpy()), "host/device legs disagree"
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    fp64_tflops = eng.fp64_probe(4096)
+    dom = max((k for k in ktimes if k in KERNEL_ALGO), key=lambda k: ktimes[k])
+    kern = {}
+    for k, ms in ktimes.items():
+        ab, fl = KERNEL_ALGO.get(k, (0.0, 0.0))
+        kern[k] = {"ms": ms, "share": ms / max(1e-9, sum(ktimes.values())),
+                   "hbm_gbs": ab * units_rank / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                   "fp64_tflops": fl * units_rank / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
+    achieved = kern[dom]["hbm_gbs"]
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_trajectory_day": KERNEL_ALGO[dom][0],
+                "fp64": {"achieved_tflops": kern[dom]["fp64_tflops"], "peak_tflops_measured": fp64_tflops,
+                         "frac": kern[dom]["fp64_tflops"] / fp64_tflops if fp64_tflops else None,
+                         "canonical_flops_per_trajectory_day": KERNEL_ALGO[dom][1]},
+                "step": {"hbm_frac": BYTES_FUSED_M6 * units_rank / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                         "fp64_frac": FLOPS_EKF_EKS_M6 * units_rank / (ms_step * 1e-3) / 1e12 / fp64_tflops
+                         if fp64_tflops else None},
+                "kernels": kern}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import oracle as orc
+        n, cores, _ = cpu_sample(a, inp, eps, a.cpu_seconds)
+        sample = inp[:n]
+        regs = oracle_regions(sample, S_fixed[:, :, :n])
+        t0 = time.perf_counter()
+        j0, j1, _, _ = orc.sweep_batch(regs, eps, n_threads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n * nE * T / dt, "unit": "trajectory-days/s", "cores": cores, "kind": "port",
+               "sample": f"{n} of {nR} regions x {nE} eps x {T} days, {dt:.1f} s (C oracle, OpenMP)",
+               "parity_with_gpu_bit_exact": bool(np.array_equal(j0, out["J0"].cpu().numpy()[:n]) and
+                                                 np.array_equal(j1, out["J1"].cpu().numpy()[:n]))}
+
+    if rank == 0:
+        line = {"metric": "trajectory_days_per_sec", "value": value, "unit": "trajectory-days/s", "n_gpus": world,
+                "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "trajectories_per_gpu": nR * nE, "days": T,
+                           "parallelism": f"regions replicated per GPU x{world} (weak); one all-gather of (J0,J1)",
+                           "l2": "per-step tape traffic (>30 GB) far exceeds the 126 MB L2; no explicit flush",
+                           "mode_value": "EPI_MEM_DEVICE (inputs resident in HBM)",
+                           "mode_e2e": "EPI_MEM_HOST (pinned host buffers, blocking call)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

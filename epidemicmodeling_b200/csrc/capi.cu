@@ -1,0 +1,808 @@
+// capi.cu -- the C ABI of libepi_b200.so (include/epi_b200.h): argument
+// validation, host<->device staging, wave scheduling over the scratch budget,
+// kernel sequencing and per-phase device timing.  No exception crosses the
+// boundary; there is no CPU fallback (epi_create fails without a CUDA device).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "epi_device.cuh"
+#include "epi_internal.h"
+
+using namespace epi;
+
+namespace {
+
+struct EpiError {
+  int code;
+  std::string msg;
+};
+
+thread_local std::string g_create_err;
+
+struct Phase {
+  const char *name;
+  cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct epi_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+  size_t scratch_limit = 0;
+  long long launches = 0;
+  std::vector<Phase> phases;       // of the most recent batched call
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+namespace {
+
+#define CK(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      char buf_[512];                                                                  \
+      snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+               __FILE__, __LINE__);                                                    \
+      throw EpiError{e_ == cudaErrorMemoryAllocation ? EPI_ERR_NOMEM : EPI_ERR_CUDA, buf_}; \
+    }                                                                                  \
+  } while (0)
+
+[[noreturn]] void bad_arg(const std::string &m, int code = EPI_ERR_ARG) { throw EpiError{code, m}; }
+
+cudaEvent_t get_event(epi_ctx *c) {
+  if (!c->ev_pool.empty()) {
+    cudaEvent_t e = c->ev_pool.back();
+    c->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CK(cudaEventCreate(&e));
+  return e;
+}
+void reset_phases(epi_ctx *c) {
+  for (auto &p : c->phases) { c->ev_pool.push_back(p.a); c->ev_pool.push_back(p.b); }
+  c->phases.clear();
+}
+struct PhaseScope {
+  epi_ctx *c;
+  Phase ph;
+  PhaseScope(epi_ctx *ctx, const char *name) : c(ctx) {
+    ph.name = name; ph.a = get_event(c); ph.b = get_event(c);
+    CK(cudaEventRecord(ph.a, c->stream));
+  }
+  void end() {
+    CK(cudaEventRecord(ph.b, c->stream));
+    c->phases.push_back(ph);
+  }
+};
+
+// one batched call (or one wave of it): owns the staging buffers it allocated
+// and the list of device->host copies to issue once the kernels are enqueued.
+struct Call {
+  epi_ctx *c;
+  int mem;
+  std::vector<void *> dev;
+  struct Copy { void *dst; const void *src; size_t dpitch, spitch, width, height; };
+  std::vector<Copy> pend;
+
+  Call(epi_ctx *ctx, int m) : c(ctx), mem(m) {}
+  ~Call() { release(); }
+  Call(const Call &) = delete;
+
+  void *dalloc(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0) bytes = 8;
+    CK(cudaMallocAsync(&p, bytes, c->stream));
+    dev.push_back(p);
+    return p;
+  }
+  void release() {
+    for (void *p : dev) cudaFreeAsync(p, c->stream);
+    dev.clear();
+  }
+  // whole-array input of n elements (per-group tables etc.)
+  template <class T>
+  const T *in(const T *p, size_t n) {
+    if (!p || mem == EPI_MEM_DEVICE) return p;
+    T *d = (T *)dalloc(n * sizeof(T));
+    CK(cudaMemcpyAsync(d, p, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    return d;
+  }
+  // whole-array output of n elements
+  template <class T>
+  T *out(T *p, size_t n) {
+    if (!p || mem == EPI_MEM_DEVICE) return p;
+    T *d = (T *)dalloc(n * sizeof(T));
+    pend.push_back({p, d, n * sizeof(T), n * sizeof(T), n * sizeof(T), 1});
+    return d;
+  }
+  // per-trajectory input [rows][B]: the slice [b0, b0+Bw) of every row
+  template <class T>
+  const T *traj_in_raw(const T *p, size_t rows, long long B, long long b0, long long Bw,
+                       long long *stride, long long *off) {
+    if (!p) { *stride = 0; *off = 0; return nullptr; }
+    if (mem == EPI_MEM_DEVICE) { *stride = B; *off = b0; return p; }
+    T *d = (T *)dalloc(rows * (size_t)Bw * sizeof(T));
+    CK(cudaMemcpy2DAsync(d, (size_t)Bw * sizeof(T), p + b0, (size_t)B * sizeof(T),
+                         (size_t)Bw * sizeof(T), rows, cudaMemcpyHostToDevice, c->stream));
+    *stride = Bw; *off = 0;
+    return d;
+  }
+  CArr traj_in(const double *p, size_t rows, long long B, long long b0, long long Bw) {
+    CArr a;
+    a.p = traj_in_raw<double>(p, rows, B, b0, Bw, &a.stride, &a.off);
+    return a;
+  }
+  // per-trajectory output [rows][B]
+  TArr traj_out(double *p, size_t rows, long long B, long long b0, long long Bw) {
+    if (!p) return TArr{nullptr, 0, 0};
+    if (mem == EPI_MEM_DEVICE) return TArr{p, B, b0};
+    double *d = (double *)dalloc(rows * (size_t)Bw * sizeof(double));
+    pend.push_back({p + b0, d, (size_t)B * sizeof(double), (size_t)Bw * sizeof(double),
+                    (size_t)Bw * sizeof(double), rows});
+    return TArr{d, Bw, 0};
+  }
+  // library scratch [rows][Bw]
+  TArr scratch(size_t rows, long long Bw) {
+    return TArr{(double *)dalloc(rows * (size_t)Bw * sizeof(double)), Bw, 0};
+  }
+  void flush() {
+    for (auto &k : pend)
+      CK(cudaMemcpy2DAsync(k.dst, k.dpitch, k.src, k.spitch, k.width, k.height,
+                           cudaMemcpyDeviceToHost, c->stream));
+    pend.clear();
+  }
+};
+
+void check_launch(epi_ctx *c, int n) {
+  c->launches += n;
+  CK(cudaGetLastError());
+}
+
+size_t scratch_budget(epi_ctx *c) {
+  if (c->scratch_limit) return c->scratch_limit;
+  size_t fr = 0, tot = 0;
+  CK(cudaMemGetInfo(&fr, &tot));
+  // memory cached in the stream-ordered pool counts as "used" in cudaMemGetInfo
+  cudaMemPool_t pool;
+  unsigned long long reserved = 0, used = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+  }
+  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0);
+  return (size_t)(0.6 * (double)avail);
+}
+
+long long wave_size(long long B, size_t bytes_per_traj, size_t budget) {
+  if (bytes_per_traj == 0) return B;
+  long long w = (long long)(budget / bytes_per_traj);
+  if (w >= B) return B;
+  if (w >= 4096) w -= w % 1024;
+  else if (w >= 64) w -= w % 32;
+  if (w < 1) bad_arg("scratch limit too small for a single trajectory", EPI_ERR_NOMEM);
+  return w;
+}
+
+template <class F>
+int guarded(epi_ctx *ctx, F &&f) {
+  if (!ctx) return EPI_ERR_ARG;
+  try {
+    CK(cudaSetDevice(ctx->device));
+    f();
+    ctx->err.clear();
+    return EPI_OK;
+  } catch (const EpiError &e) {
+    ctx->err = e.msg;
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    ctx->err = e.what();
+    return EPI_ERR_ARG;
+  }
+}
+
+void check_mem(int mem) {
+  if (mem != EPI_MEM_HOST && mem != EPI_MEM_DEVICE) bad_arg("mem must be EPI_MEM_HOST or EPI_MEM_DEVICE");
+}
+
+void finish(epi_ctx *c, int mem) {
+  if (mem == EPI_MEM_HOST) CK(cudaStreamSynchronize(c->stream));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int epi_create(int device, epi_ctx **out) {
+  if (!out) return EPI_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_err = std::string("no CUDA device available (") +
+                   (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                   "): libepi_b200 has no CPU fallback";
+    cudaGetLastError();
+    return EPI_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) {
+    g_create_err = "device index out of range";
+    return EPI_ERR_ARG;
+  }
+  epi_ctx *c = new epi_ctx;
+  c->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(e);
+    delete c;
+    return EPI_ERR_CUDA;
+  }
+  c->stream = c->own_stream;
+  // keep freed staging/scratch memory cached in the stream-ordered pool
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = c;
+  g_create_err.clear();
+  return EPI_OK;
+}
+
+extern "C" void epi_destroy(epi_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  reset_phases(c);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+extern "C" const char *epi_last_error(const epi_ctx *c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int epi_set_stream(epi_ctx *c, void *s) {
+  if (!c) return EPI_ERR_ARG;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return EPI_OK;
+}
+
+extern "C" int epi_sync(epi_ctx *c) {
+  return guarded(c, [&] { CK(cudaStreamSynchronize(c->stream)); });
+}
+
+extern "C" int epi_set_scratch_limit(epi_ctx *c, size_t bytes) {
+  if (!c) return EPI_ERR_ARG;
+  c->scratch_limit = bytes;
+  return EPI_OK;
+}
+
+extern "C" long long epi_launch_count(const epi_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int epi_last_kernel_times(epi_ctx *c, float *ms, const char **names, int max) {
+  if (!c) return 0;
+  int n = 0;
+  for (auto &p : c->phases) {
+    if (cudaEventSynchronize(p.b) != cudaSuccess) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.a, p.b) != cudaSuccess) continue;
+    int k = 0;
+    for (; k < n; ++k)
+      if (!strcmp(names[k], p.name)) break;
+    if (k == n) {
+      if (n >= max) continue;
+      names[n] = p.name; ms[n] = 0.f; ++n;
+    }
+    ms[k] += t;
+  }
+  return n;
+}
+
+extern "C" int epi_fp64_probe(epi_ctx *c, int iters, double *tflops) {
+  return guarded(c, [&] {
+    if (iters < 1 || !tflops) bad_arg("epi_fp64_probe: bad arguments");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    Call k(c, EPI_MEM_DEVICE);
+    double *out = (double *)k.dalloc((size_t)blocks * threads * sizeof(double));
+    launch_fp64_probe(out, blocks, threads, 16, c->stream);  // warm-up
+    check_launch(c, 1);
+    cudaEvent_t a = get_event(c), b = get_event(c);
+    CK(cudaEventRecord(a, c->stream));
+    launch_fp64_probe(out, blocks, threads, iters, c->stream);
+    check_launch(c, 1);
+    CK(cudaEventRecord(b, c->stream));
+    CK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    c->ev_pool.push_back(a); c->ev_pool.push_back(b);
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / ((double)ms * 1e-3) / 1e12;
+  });
+}
+
+// ---------------------------------------------------------------------------
+// SEIRP
+// ---------------------------------------------------------------------------
+extern "C" int epi_seirp_batch(epi_ctx *c, const epi_seirp_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->K < 0) bad_arg("epi_seirp_batch: B and K must be >= 0");
+    if (a->rate_mode < EPI_RATES_CONST || a->rate_mode > EPI_RATES_SERIES) bad_arg("epi_seirp_batch: bad rate_mode");
+    if (a->out_mode != EPI_SEIRP_OUT_FULL && a->out_mode != EPI_SEIRP_OUT_FINAL) bad_arg("epi_seirp_batch: bad out_mode");
+    if (a->B == 0 || a->K == 0) return;
+    if (!a->rates || !a->ic || !a->out) bad_arg("epi_seirp_batch: rates, ic and out are required");
+    reset_phases(c);
+    const long long B = a->B;
+    const int K = a->K;
+    const size_t rate_rows = a->rate_mode == EPI_RATES_SERIES ? (size_t)7 * K : (a->rate_mode == EPI_RATES_CONST ? 7 : 0);
+    const size_t out_rows = a->out_mode == EPI_SEIRP_OUT_FULL ? (size_t)5 * K : 5;
+    Call shared(c, a->mem);
+    const double *rates_shared =
+        a->rate_mode == EPI_RATES_SHARED_SERIES ? shared.in(a->rates, (size_t)7 * K) : nullptr;
+    const long long Bw = a->mem == EPI_MEM_HOST
+                             ? wave_size(B, (rate_rows + 5 + out_rows) * sizeof(double), scratch_budget(c))
+                             : B;
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      SeirpParams p{};
+      p.B = (int)nb; p.K = K; p.rate_mode = a->rate_mode; p.saturated = a->saturated; p.out_mode = a->out_mode;
+      p.dt = a->dt; p.beta_0 = a->beta_0; p.beta_s = a->beta_s; p.mu_0 = a->mu_0; p.mu_s = a->mu_s;
+      p.sigma = a->sigma; p.i_0 = a->i_0;
+      p.rates = rate_rows ? w.traj_in(a->rates, rate_rows, B, b0, nb) : CArr{nullptr, 0, 0};
+      p.rates_shared = rates_shared;
+      p.ic = w.traj_in(a->ic, 5, B, b0, nb);
+      p.out = w.traj_out(a->out, out_rows, B, b0, nb);
+      PhaseScope ph(c, "seirp");
+      launch_seirp(p, c->stream);
+      check_launch(c, 1);
+      ph.end();
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
+// ---------------------------------------------------------------------------
+// SIalpha_Controlled + NPICost
+// ---------------------------------------------------------------------------
+extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->K < 0 || a->G < 1) bad_arg("epi_rollout_cost_batch: bad B/K/G");
+    if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_rollout_cost_batch: L must be in 1..12");
+    if (a->u_kind != EPI_U_F64 && a->u_kind != EPI_U_U8) bad_arg("epi_rollout_cost_batch: bad u_kind");
+    if ((a->J0 == nullptr) != (a->J1 == nullptr)) bad_arg("epi_rollout_cost_batch: J0 and J1 go together");
+    if (a->B == 0) return;
+    if (!a->prm || !a->x0 || (a->K > 0 && !a->u)) bad_arg("epi_rollout_cost_batch: prm, x0 and u are required");
+    if (a->J0 && a->T_total < 1) bad_arg("epi_rollout_cost_batch: T_total must be >= 1 when costs are requested");
+    reset_phases(c);
+    const long long B = a->B;
+    const int K = a->K, L = a->L;
+    const long long n_groups = (B + a->G - 1) / a->G;
+    Call shared(c, a->mem);
+    const epi_model_params *prm = shared.in(a->prm, (size_t)n_groups);
+    const double *x0 = shared.in(a->x0, (size_t)3 * n_groups);
+    const double *nstd = shared.in(a->noise_std, (size_t)3 * n_groups);
+    const double *j0p = shared.in(a->j0_prefix, (size_t)n_groups);
+    const double *j1p = shared.in(a->j1_prefix, (size_t)n_groups);
+    const double *wts = shared.in(a->w, (size_t)n_groups * K * L);
+    const size_t usz = a->u_kind == EPI_U_F64 ? 8 : 1;
+    size_t per = (size_t)K * L * usz + (a->noise ? (size_t)K * 24 : 0) +
+                 ((a->s ? 1 : 0) + (a->i ? 1 : 0) + (a->alpha ? 1 : 0)) * (size_t)K * 8 + 16;
+    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, per, scratch_budget(c)) : B;
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      RolloutParams p{};
+      p.B = (int)nb; p.K = K; p.L = L; p.G = a->G; p.b0 = b0;
+      p.prm = prm; p.x0 = x0; p.noise_std = nstd;
+      p.u_kind = a->u_kind;
+      if (a->u_kind == EPI_U_F64)
+        p.u = w.traj_in_raw<double>((const double *)a->u, (size_t)K * L, B, b0, nb, &p.u_stride, &p.u_off);
+      else
+        p.u = w.traj_in_raw<unsigned char>((const unsigned char *)a->u, (size_t)K * L, B, b0, nb, &p.u_stride, &p.u_off);
+      p.noise = w.traj_in(a->noise, (size_t)K * 3, B, b0, nb);
+      p.s = w.traj_out(a->s, K, B, b0, nb);
+      p.i = w.traj_out(a->i, K, B, b0, nb);
+      p.alpha = w.traj_out(a->alpha, K, B, b0, nb);
+      p.T_total = a->T_total; p.T_hist = 0;
+      p.j0_prefix = j0p; p.j1_prefix = j1p; p.w = wts;
+      p.J0 = w.traj_out(a->J0, 1, B, b0, nb);
+      p.J1 = w.traj_out(a->J1, 1, B, b0, nb);
+      PhaseScope ph(c, "rollout_cost");
+      launch_rollout(p, c->stream);
+      check_launch(c, 1);
+      ph.end();
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
+extern "C" int epi_npicost_batch(epi_ctx *c, const epi_npicost_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->T < 1 || a->G < 1) bad_arg("epi_npicost_batch: bad B/T/G");
+    if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_npicost_batch: L must be in 1..12");
+    if (a->B == 0) return;
+    if (!a->newcases || !a->inputs || !a->weights || !a->J0 || !a->J1) bad_arg("epi_npicost_batch: null array");
+    reset_phases(c);
+    const long long B = a->B;
+    const long long n_groups = (B + a->G - 1) / a->G;
+    Call shared(c, a->mem);
+    const double *wts = shared.in(a->weights, (size_t)n_groups * a->T * a->L);
+    const long long Bw = a->mem == EPI_MEM_HOST
+                             ? wave_size(B, ((size_t)a->T * (a->L + 1) + 2) * 8, scratch_budget(c)) : B;
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      CostParams p{};
+      p.B = (int)nb; p.T = a->T; p.L = a->L; p.G = a->G; p.b0 = b0;
+      p.newcases = w.traj_in(a->newcases, a->T, B, b0, nb);
+      p.inputs = w.traj_in(a->inputs, (size_t)a->T * a->L, B, b0, nb);
+      p.weights = wts;
+      p.J0 = w.traj_out(a->J0, 1, B, b0, nb);
+      p.J1 = w.traj_out(a->J1, 1, B, b0, nb);
+      PhaseScope ph(c, "npicost");
+      launch_npicost(p, c->stream);
+      check_launch(c, 1);
+      ph.end();
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
+extern "C" int epi_si_controlled_batch(epi_ctx *c, const epi_si_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->K < 0) bad_arg("epi_si_controlled_batch: bad B/K");
+    if (a->B == 0 || a->K == 0) return;
+    if (!a->alpha || !a->beta || !a->s0 || !a->i0 || !a->s || !a->i) bad_arg("epi_si_controlled_batch: null array");
+    reset_phases(c);
+    const long long B = a->B;
+    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, ((size_t)3 * a->K + 3) * 8, scratch_budget(c)) : B;
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      SiParams p{};
+      p.B = (int)nb; p.K = a->K; p.dt = a->dt;
+      p.alpha = w.traj_in(a->alpha, a->K, B, b0, nb);
+      p.beta = w.traj_in(a->beta, 1, B, b0, nb);
+      p.s0 = w.traj_in(a->s0, 1, B, b0, nb);
+      p.i0 = w.traj_in(a->i0, 1, B, b0, nb);
+      p.s = w.traj_out(a->s, a->K, B, b0, nb);
+      p.i = w.traj_out(a->i, a->K, B, b0, nb);
+      PhaseScope ph(c, "si_controlled");
+      launch_si(p, c->stream);
+      check_launch(c, 1);
+      ph.end();
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
+// ---------------------------------------------------------------------------
+// EKF + smoother
+// ---------------------------------------------------------------------------
+namespace {
+
+void validate_params_host(const epi_model_params *prm, long long n, int L, int model) {
+  for (long long g = 0; g < n; ++g) {
+    if (prm[g].L != L) bad_arg("epi_model_params.L does not match args.L");
+    if (model != EPI_MODEL_LEGACY_CODEGEN && prm[g].obs_type != EPI_OBS_NEWCASES &&
+        prm[g].obs_type != EPI_OBS_TOTALCASES)
+      bad_arg("unknown observation type", EPI_ERR_OBS_TYPE);  // SIAlphaModelEKF.m:57,87
+  }
+}
+
+}  // namespace
+
+extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->model < EPI_MODEL_SIALPHA || a->model > EPI_MODEL_LEGACY_CODEGEN) bad_arg("epi_ekf_eks_batch: unknown model");
+    if (a->order != 1 && a->order != 2) bad_arg("Undefined order", EPI_ERR_ORDER);  // GenericEKF.m:111,151
+    if (a->B < 0 || a->T < 1 || a->G < 1 || a->W < 1) bad_arg("epi_ekf_eks_batch: bad B/T/G/W");
+    if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_ekf_eks_batch: L must be in 1..12");
+    if (a->q_mode < EPI_Q_CONST || a->q_mode > EPI_Q_PERDAY_FULL)
+      bad_arg("Process noise covariance noise mismatch", EPI_ERR_QR_SHAPE);  // :75
+    if (a->r_mode != EPI_R_CONST && a->r_mode != EPI_R_PERDAY)
+      bad_arg("Observation noise covariance noise mismatch", EPI_ERR_QR_SHAPE);  // :90
+    const bool legacy = model_legacy(a->model);
+    if (legacy && (a->q_mode != EPI_Q_CONST || a->r_mode != EPI_R_CONST))
+      bad_arg("the legacy estimator takes a constant Q and a scalar R", EPI_ERR_QR_SHAPE);
+    if (a->B == 0) return;
+    if (!a->prm || !a->u || !a->x || !a->R || !a->Q || !a->s_init || !a->Ps_init || !a->s_final || !a->Ps_final)
+      bad_arg("epi_ekf_eks_batch: a required input array is null");
+    reset_phases(c);
+    const int M = model_dim(a->model), MM = M * M, T = a->T, L = a->L;
+    const long long B = a->B;
+    const long long n_groups = (B + a->G - 1) / a->G;
+    if (a->mem == EPI_MEM_HOST) validate_params_host(a->prm, n_groups, L, a->model);
+
+    Call shared(c, a->mem);
+    const epi_model_params *prm = shared.in(a->prm, (size_t)n_groups);
+    const double *u_grp = a->u_per_traj ? nullptr : shared.in(a->u, (size_t)n_groups * T * L);
+    const double *x_grp = a->x_per_traj ? nullptr : shared.in(a->x, (size_t)n_groups * T);
+    const double *R_grp = a->r_per_traj ? nullptr
+                                        : shared.in(a->R, (size_t)n_groups * (a->r_mode == EPI_R_CONST ? 1 : T));
+    const size_t q_per = a->q_mode == EPI_Q_CONST ? (size_t)MM : a->q_mode == EPI_Q_PERDAY_SCALAR ? (size_t)T : (size_t)T * MM;
+    const double *Q = shared.in(a->Q, (size_t)n_groups * q_per);
+    const double *s_init_g = nullptr, *Ps_init_g = nullptr, *s_final_g = nullptr, *Ps_final_g = nullptr;
+    if (!a->init_per_traj) {
+      s_init_g = shared.in(a->s_init, (size_t)n_groups * M);
+      Ps_init_g = shared.in(a->Ps_init, (size_t)n_groups * MM);
+      s_final_g = shared.in(a->s_final, (size_t)n_groups * M);
+      Ps_final_g = shared.in(a->Ps_final, (size_t)n_groups * MM);
+    }
+
+    // scratch / staging bytes per trajectory
+    const bool host = a->mem == EPI_MEM_HOST;
+    const bool packed = !legacy && !a->P_MINUS && !a->P_PLUS;
+    const int PF = packed ? M * (M + 1) / 2 : MM;
+    size_t per = (size_t)(T - 1) * MM * 8;  // J
+    if (!a->S_MINUS || host) per += (size_t)T * M * 8;
+    if (!a->S_PLUS || host) per += (size_t)T * M * 8;
+    if (!a->P_MINUS || host) per += (size_t)T * PF * 8;
+    if (!a->P_PLUS || host) per += (size_t)T * PF * 8;
+    if (host) {
+      if (a->u_per_traj) per += (size_t)T * L * 8;
+      if (a->x_per_traj) per += (size_t)T * 8;
+      if (a->r_per_traj) per += (size_t)(a->r_mode == EPI_R_CONST ? 1 : T) * 8;
+      if (a->init_per_traj) per += (size_t)(2 * M + 2 * MM) * 8;
+      per += ((a->u_opt ? 1 : 0) + (a->u_opt_smooth ? 1 : 0)) * (size_t)T * L * 8;
+      per += ((a->S_SMOOTH ? 1 : 0) + (a->K_GAIN ? 1 : 0)) * (size_t)T * M * 8;
+      per += (a->P_SMOOTH ? (size_t)T * MM * 8 : 0);
+      per += ((a->innovations ? 1 : 0) + (a->rho ? 1 : 0)) * (size_t)T * 8 + 16;
+    }
+    const long long Bw = wave_size(B, per, scratch_budget(c));
+
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      EkfParams p{};
+      p.model = a->model; p.B = (int)nb; p.T = T; p.L = L; p.G = a->G; p.W = a->W; p.b0 = b0;
+      p.prm = prm;
+      p.epsilon = w.traj_in(a->epsilon, 1, B, b0, nb);
+      p.eps_grid = nullptr; p.eps_mod = 1;
+      p.u_grp = u_grp; p.x_grp = x_grp; p.R_grp = R_grp;
+      p.u_trj = a->u_per_traj ? w.traj_in(a->u, (size_t)T * L, B, b0, nb) : CArr{nullptr, 0, 0};
+      p.x_trj = a->x_per_traj ? w.traj_in(a->x, T, B, b0, nb) : CArr{nullptr, 0, 0};
+      p.R_trj = a->r_per_traj ? w.traj_in(a->R, a->r_mode == EPI_R_CONST ? 1 : T, B, b0, nb) : CArr{nullptr, 0, 0};
+      p.r_mode = a->r_mode; p.fixed_R = a->fixed_R; p.q_mode = a->q_mode; p.Q = Q;
+      p.init_per_traj = a->init_per_traj;
+      p.s_init_g = s_init_g; p.Ps_init_g = Ps_init_g; p.s_final_g = s_final_g; p.Ps_final_g = Ps_final_g;
+      if (a->init_per_traj) {
+        p.s_init_t = w.traj_in(a->s_init, M, B, b0, nb);
+        p.Ps_init_t = w.traj_in(a->Ps_init, MM, B, b0, nb);
+        p.s_final_t = w.traj_in(a->s_final, M, B, b0, nb);
+        p.Ps_final_t = w.traj_in(a->Ps_final, MM, B, b0, nb);
+      }
+      p.v_bar = a->v_bar; p.beta = a->beta; p.gamma = a->gamma;
+      p.tape_packed = packed ? 1 : 0;
+      p.S_MINUS = a->S_MINUS ? w.traj_out(a->S_MINUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
+      p.S_PLUS = a->S_PLUS ? w.traj_out(a->S_PLUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
+      p.P_MINUS = a->P_MINUS ? w.traj_out(a->P_MINUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * PF, nb);
+      p.P_PLUS = a->P_PLUS ? w.traj_out(a->P_PLUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * PF, nb);
+      p.J = w.scratch((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
+      p.u_opt = w.traj_out(a->u_opt, (size_t)T * L, B, b0, nb);
+      p.u_opt_smooth = legacy ? TArr{nullptr, 0, 0} : w.traj_out(a->u_opt_smooth, (size_t)T * L, B, b0, nb);
+      p.S_SMOOTH = w.traj_out(a->S_SMOOTH, (size_t)T * M, B, b0, nb);
+      p.P_SMOOTH = w.traj_out(a->P_SMOOTH, (size_t)T * MM, B, b0, nb);
+      p.K_GAIN = w.traj_out(a->K_GAIN, (size_t)T * M, B, b0, nb);
+      p.innov = w.traj_out(a->innovations, T, B, b0, nb);
+      p.rho = w.traj_out(a->rho, T, B, b0, nb);
+      p.status = nullptr;
+      if (a->status) {
+        if (host) {
+          p.status = (int *)w.dalloc((size_t)nb * sizeof(int));
+          w.pend.push_back({a->status + b0, p.status, (size_t)nb * 4, (size_t)nb * 4, (size_t)nb * 4, 1});
+        } else {
+          p.status = a->status + b0;
+        }
+        CK(cudaMemsetAsync(p.status, 0, (size_t)nb * sizeof(int), c->stream));
+      }
+      p.T_hist = 0;
+      {
+        PhaseScope ph(c, "ekf_forward");
+        launch_ekf_forward(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      if (T > 1) {
+        PhaseScope ph(c, "eks_gain");
+        launch_eks_gain(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      {
+        PhaseScope ph(c, "eks_backward");
+        launch_eks_backward(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
+// ---------------------------------------------------------------------------
+// Pareto
+// ---------------------------------------------------------------------------
+extern "C" int epi_pareto_batch(epi_ctx *c, const epi_pareto_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->n_sets < 0 || a->n < 0) bad_arg("epi_pareto_batch: bad sizes");
+    if (a->n_sets == 0 || a->n == 0) return;
+    if (!a->J0 || !a->J1) bad_arg("epi_pareto_batch: J0 and J1 are required");
+    if ((size_t)a->n * 16 > 200 * 1024) bad_arg("epi_pareto_batch: n too large for one CTA's shared memory (max 12800)");
+    reset_phases(c);
+    Call k(c, a->mem);
+    const size_t tot = (size_t)a->n_sets * a->n;
+    ParetoParams p{};
+    p.n_sets = a->n_sets; p.n = a->n;
+    p.J0 = k.in(a->J0, tot); p.J1 = k.in(a->J1, tot);
+    p.on_front = k.out(a->on_front, tot);
+    p.I_opt = k.out(a->I_opt, (size_t)a->n_sets);
+    PhaseScope ph(c, "pareto");
+    launch_pareto(p, c->stream);
+    check_launch(c, 1);
+    ph.end();
+    k.flush();
+    finish(c, a->mem);
+  });
+}
+
+// ---------------------------------------------------------------------------
+// fused optimal-NPI Pareto sweep
+// ---------------------------------------------------------------------------
+extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->n_regions < 0 || a->n_eps < 1 || a->T < 1 || a->T_hist < 0 || a->T_hist > a->T || a->W < 1)
+      bad_arg("epi_sweep: bad sizes");
+    if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_sweep: L must be in 1..12");
+    if (a->n_regions == 0) return;
+    if (!a->prm || !a->eps || !a->u || !a->x || !a->R || !a->s_init || !a->Ps_init || !a->s_final ||
+        !a->Ps_final || !a->Q || !a->x0 || !a->weights || !a->J0 || !a->J1 || (a->T_hist > 0 && !a->newcases_hist))
+      bad_arg("epi_sweep: a required array is null");
+    if (a->u_knee && !a->I_opt) bad_arg("epi_sweep: u_knee needs I_opt");
+    if ((size_t)a->n_eps * 16 > 200 * 1024) bad_arg("epi_sweep: n_eps too large (max 12800)");
+    reset_phases(c);
+    const int M = 6, MM = 36, PF = 21, T = a->T, L = a->L, Tf = a->T - a->T_hist;
+    const long long nR = a->n_regions, B = nR * a->n_eps;
+    const bool host = a->mem == EPI_MEM_HOST;
+    if (host) validate_params_host(a->prm, nR, L, EPI_MODEL_OPTCTRL);
+
+    Call shared(c, a->mem);
+    const epi_model_params *prm = shared.in(a->prm, (size_t)nR);
+    const double *eps = shared.in(a->eps, (size_t)a->n_eps);
+    const double *u = shared.in(a->u, (size_t)nR * T * L);
+    const double *x = shared.in(a->x, (size_t)nR * T);
+    const double *R = shared.in(a->R, (size_t)nR * T);
+    const double *s_init = shared.in(a->s_init, (size_t)nR * M);
+    const double *Ps_init = shared.in(a->Ps_init, (size_t)nR * MM);
+    const double *s_final = shared.in(a->s_final, (size_t)nR * M);
+    const double *Ps_final = shared.in(a->Ps_final, (size_t)nR * MM);
+    const double *Q = shared.in(a->Q, (size_t)nR * MM);
+    const double *x0 = shared.in(a->x0, (size_t)nR * 3);
+    const double *nch = shared.in(a->newcases_hist, (size_t)nR * a->T_hist);
+    const double *wts = shared.in(a->weights, (size_t)nR * T * L);
+    const double *nstd = shared.in(a->noise_std, (size_t)nR * 3);
+    // whole-batch outputs (the Pareto step needs every epsilon of a region)
+    double *J0 = shared.out(a->J0, (size_t)B);
+    double *J1 = shared.out(a->J1, (size_t)B);
+    unsigned char *on_front = shared.out(a->on_front, (size_t)B);
+    int *I_opt = shared.out(a->I_opt, (size_t)nR);
+    double *u_knee = shared.out(a->u_knee, (size_t)nR * Tf * L);
+    // the knee gather needs every smoothed schedule on the device
+    double *u_fore_dev = nullptr;
+    if (a->u_fore && !host) u_fore_dev = a->u_fore;
+    else if (a->u_fore || a->u_knee) { u_fore_dev = (double *)shared.dalloc((size_t)Tf * L * B * 8); }
+    if (a->u_fore && host)
+      shared.pend.push_back({a->u_fore, u_fore_dev, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, 1});
+
+    size_t per = (size_t)(T - 1) * MM * 8 + (size_t)2 * T * M * 8 + (size_t)2 * T * PF * 8 + (size_t)2 * T * 8;
+    if (host && a->noise) per += (size_t)Tf * 24;
+    if (host && a->P_first) per += (size_t)MM * 8;
+    const long long Bw = wave_size(B, per, scratch_budget(c));
+
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      EkfParams p{};
+      p.model = EPI_MODEL_OPTCTRL; p.B = (int)nb; p.T = T; p.L = L; p.G = a->n_eps; p.W = a->W; p.b0 = b0;
+      p.prm = prm;
+      p.epsilon = CArr{nullptr, 0, 0};
+      p.eps_grid = eps; p.eps_mod = a->n_eps;
+      p.u_grp = u; p.x_grp = x; p.R_grp = R;
+      p.r_mode = EPI_R_PERDAY; p.fixed_R = 0; p.q_mode = EPI_Q_CONST; p.Q = Q;
+      p.init_per_traj = 0;
+      p.s_init_g = s_init; p.Ps_init_g = Ps_init; p.s_final_g = s_final; p.Ps_final_g = Ps_final;
+      p.v_bar = 0.0; p.beta = a->beta_ekf; p.gamma = a->gamma_ekf;
+      p.tape_packed = 1;
+      p.S_MINUS = w.scratch((size_t)T * M, nb);
+      p.S_PLUS = w.scratch((size_t)T * M, nb);
+      p.P_MINUS = w.scratch((size_t)T * PF, nb);
+      p.P_PLUS = w.scratch((size_t)T * PF, nb);
+      p.J = w.scratch((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
+      p.dot_day = w.scratch(T, nb);
+      p.cost_day = w.scratch(T, nb);
+      p.weights = wts;
+      p.T_hist = a->T_hist;
+      if (u_fore_dev) p.u_fore = TArr{u_fore_dev, B, b0};
+      p.P_first = w.traj_out(a->P_first, MM, B, b0, nb);
+      {
+        PhaseScope ph(c, "ekf_forward");
+        launch_ekf_forward(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      if (T > 1) {
+        PhaseScope ph(c, "eks_gain");
+        launch_eks_gain(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      {
+        PhaseScope ph(c, "eks_backward");
+        launch_eks_backward(p, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      RolloutParams r{};
+      r.B = (int)nb; r.K = Tf; r.L = L; r.G = a->n_eps; r.b0 = b0;
+      r.prm = prm; r.x0 = x0; r.noise_std = nstd;
+      r.u_kind = 2;
+      r.noise = w.traj_in(a->noise, (size_t)Tf * 3, B, b0, nb);
+      r.T_total = T; r.T_hist = a->T_hist;
+      r.newcases_hist = nch;
+      r.dot_day = CArr{p.dot_day.p, p.dot_day.stride, p.dot_day.off};
+      r.cost_day = CArr{p.cost_day.p, p.cost_day.stride, p.cost_day.off};
+      r.J0 = TArr{J0, B, b0};
+      r.J1 = TArr{J1, B, b0};
+      {
+        PhaseScope ph(c, "rollout_cost");
+        launch_rollout(r, c->stream);
+        check_launch(c, 1);
+        ph.end();
+      }
+      w.flush();
+    }
+    if (on_front || I_opt) {
+      ParetoParams pp{};
+      pp.n_sets = (int)nR; pp.n = a->n_eps; pp.J0 = J0; pp.J1 = J1; pp.on_front = on_front; pp.I_opt = I_opt;
+      PhaseScope ph(c, "pareto");
+      launch_pareto(pp, c->stream);
+      check_launch(c, 1);
+      if (u_knee) {
+        launch_gather_knee(u_fore_dev, I_opt, u_knee, (int)nR, a->n_eps, Tf, L, c->stream);
+        check_launch(c, 1);
+      }
+      ph.end();
+    }
+    shared.flush();
+    finish(c, a->mem);
+  });
+}

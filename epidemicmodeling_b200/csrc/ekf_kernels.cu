@@ -33,6 +33,37 @@ EPI_DI size_t cidx(const CArr &a, int t, int f, int F, int b) {
   return ((size_t)t * F + f) * (size_t)a.stride + (size_t)a.off + b;
 }
 
+// covariance tape pages: full column-major m x m (caller-visible outputs) or,
+// for library scratch of the generic (exactly symmetric) models, the packed
+// upper triangle -- 21 instead of 36 doubles per page for m = 6.
+template <int M, bool SYM>
+EPI_DI void store_tape(const Mat<M, SYM> &Pm, const TArr &a, int t, int b, bool packed) {
+  if (SYM && packed) {
+    constexpr int N = Mat<M, true>::N;
+    double *base = a.p + ((size_t)t * N) * (size_t)a.stride + (size_t)a.off + b;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = i; j < M; ++j) base[(size_t)Mat<M, true>::idx(i, j) * (size_t)a.stride] = Pm(i, j);
+  } else {
+    store_mat<M, SYM>(Pm, a.p + tidx(a, t, 0, M * M, b), (size_t)a.stride);
+  }
+}
+template <int M, bool SYM>
+EPI_DI void load_tape(Mat<M, SYM> &Pm, const TArr &a, int t, int b, bool packed) {
+  if (packed) {
+    constexpr int N = Mat<M, true>::N;
+    const double *base = a.p + ((size_t)t * N) * (size_t)a.stride + (size_t)a.off + b;
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+        if (!SYM || j >= i) Pm.at(i, j) = base[(size_t)Mat<M, true>::idx(i, j) * (size_t)a.stride];
+  } else {
+    load_mat<M, SYM>(Pm, a.p + tidx(a, t, 0, M * M, b), (size_t)a.stride);
+  }
+}
+
 // per-thread view of the per-group / per-trajectory inputs
 struct TrajIn {
   const epi_model_params *prm;
@@ -48,7 +79,8 @@ EPI_DI TrajIn traj_inputs(const EkfParams &P, int b, int M) {
   const long long gb = P.b0 + b;
   const long long g = gb / P.G;
   t.prm = P.prm + g;
-  t.eps = P.epsilon.p ? P.epsilon.p[P.epsilon.off + b] : t.prm->epsilon;
+  t.eps = P.epsilon.p ? P.epsilon.p[P.epsilon.off + b]
+          : P.eps_grid ? P.eps_grid[(int)(gb % P.eps_mod)] : t.prm->epsilon;
   if (P.u_trj.p) { t.u = P.u_trj.p + P.u_trj.off + b; t.u_js = (size_t)P.u_trj.stride; t.u_ts = (size_t)P.L * P.u_trj.stride; }
   else           { t.u = P.u_grp + (size_t)g * P.T * P.L; t.u_js = 1; t.u_ts = (size_t)P.L; }
   if (P.x_trj.p) { t.x = P.x_trj.p + P.x_trj.off + b; t.x_ts = (size_t)P.x_trj.stride; }
@@ -116,7 +148,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
     // :100-101 store the a-priori estimate
 #pragma unroll
     for (int i = 0; i < M; ++i) P.S_MINUS.p[tidx(P.S_MINUS, pos, i, M, b)] = s[i];
-    store_mat<M, SYM>(Pm, P.P_MINUS.p + tidx(P.P_MINUS, pos, 0, MM, b), (size_t)P.P_MINUS.stride);
+    store_tape<M, SYM>(Pm, P.P_MINUS, pos, b, P.tape_packed != 0);
 
     double Rk;
     if (LEG) {
@@ -232,7 +264,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
     // :167-169
 #pragma unroll
     for (int i = 0; i < M; ++i) P.S_PLUS.p[tidx(P.S_PLUS, pos, i, M, b)] = sp[i];
-    store_mat<M, SYM>(Pp, P.P_PLUS.p + tidx(P.P_PLUS, pos, 0, MM, b), (size_t)P.P_PLUS.stride);
+    store_tape<M, SYM>(Pp, P.P_PLUS, pos, b, P.tape_packed != 0);
     if (P.K_GAIN.p) {
 #pragma unroll
       for (int i = 0; i < M; ++i) P.K_GAIN.p[tidx(P.K_GAIN, pos, i, M, b)] = K[i];
@@ -309,7 +341,7 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const __grid_constant__ E
   bool bad = false;
   if (!LEG) {
     Mat<M, true> Pn, X;
-    load_mat<M, true>(Pn, P.P_MINUS.p + tidx(P.P_MINUS, posn, 0, MM, b), (size_t)P.P_MINUS.stride);
+    load_tape<M, true>(Pn, P.P_MINUS, posn, b, P.tape_packed != 0);
 #pragma unroll
     for (int q = 0; q < Mat<M, true>::N; ++q) bad |= !(fabs(Pn.v[q]) <= 1.79769313486231570815e308);  // :211
     if (bad) {
@@ -318,7 +350,7 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const __grid_constant__ E
     } else {
       rank = pinv_sym<M>(Pn, X);
       Mat<M, true> Pp;
-      load_mat<M, true>(Pp, P.P_PLUS.p + tidx(P.P_PLUS, pos, 0, MM, b), (size_t)P.P_PLUS.stride);
+      load_tape<M, true>(Pp, P.P_PLUS, pos, b, P.tape_packed != 0);
       Mat<M, false> PAt;
 #pragma unroll
       for (int i = 0; i < M; ++i)
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(128) eks_gain_kernel(const __grid_constant__ E
   store_mat<M, false>(Jm, P.J.p + tidx(P.J, k, 0, MM, b), (size_t)P.J.stride);
   if (P.status && (bad || rank < M)) {
     // max over days of ((M - rank) << 8 | guard-hit); 0 == clean, full rank everywhere
-    atomicMax(P.status + P.b0 + b, ((M - rank) << 8) | (bad ? 1 : 0));
+    atomicMax(P.status + b, ((M - rank) << 8) | (bad ? 1 : 0));
   }
 }
 
@@ -388,7 +420,7 @@ __global__ void __launch_bounds__(64) eks_backward_kernel(const __grid_constant_
   Mat<M, false> Ps;
 #pragma unroll
   for (int i = 0; i < M; ++i) ss[i] = P.S_PLUS.p[tidx(P.S_PLUS, posT, i, M, b)];
-  if (WANT_P) load_mat<M, false>(Ps, P.P_PLUS.p + tidx(P.P_PLUS, posT, 0, MM, b), (size_t)P.P_PLUS.stride);
+  if (WANT_P) load_tape<M, false>(Ps, P.P_PLUS, posT, b, SYM && P.tape_packed != 0);
   {
     double sf[M];
     Mat<M, false> Pf;
@@ -466,8 +498,8 @@ __global__ void __launch_bounds__(64) eks_backward_kernel(const __grid_constant_
     state_margins<MODEL>(prm, sk);  // :221
     if (WANT_P) {
       Mat<M, SYM> Pp, Pn;
-      load_mat<M, SYM>(Pp, P.P_PLUS.p + tidx(P.P_PLUS, pos, 0, MM, b), (size_t)P.P_PLUS.stride);
-      load_mat<M, SYM>(Pn, P.P_MINUS.p + tidx(P.P_MINUS, posn, 0, MM, b), (size_t)P.P_MINUS.stride);
+      load_tape<M, SYM>(Pp, P.P_PLUS, pos, b, SYM && P.tape_packed != 0);
+      load_tape<M, SYM>(Pn, P.P_MINUS, posn, b, SYM && P.tape_packed != 0);
       Mat<M, false> D, JD;
 #pragma unroll
       for (int i = 0; i < M; ++i)
@@ -526,8 +558,6 @@ __global__ void __launch_bounds__(64) eks_backward_kernel(const __grid_constant_
     }
   }
   if (WANT_P && P.P_first.p) {
-    const int pos0 = REV ? (T - 1) : 0;
-    (void)pos0;
     store_mat<M, false>(Ps, P.P_first.p + tidx(P.P_first, 0, 0, MM, b), (size_t)P.P_first.stride);
   }
 }

@@ -10,8 +10,9 @@ namespace epi {
 
 // A per-trajectory array in trajectory-minor layout: element (t, f, b) lives at
 // p[((size_t)t * F + f) * stride + off + b].  p == nullptr means "absent".
-// Caller-owned arrays have stride = caller's B and off = first trajectory of the
-// current wave; library scratch has stride = wave size and off = 0.
+// Caller-owned device arrays have stride = caller's B and off = first
+// trajectory of the current wave; library scratch and host-staged buffers have
+// stride = wave size and off = 0.
 struct TArr {
   double *p;
   long long stride, off;
@@ -23,13 +24,15 @@ struct CArr {
 
 // All pointers are DEVICE pointers (see include/epi_b200.h for the layouts).
 // `B` = trajectories of THIS launch (one wave of the caller's batch), `b0` =
-// index of its first trajectory in the caller's batch.
+// index of its first trajectory in the caller's batch (group = (b0 + b) / G).
 struct EkfParams {
   int model;
   int B, T, L, G, W;
   long long b0;
   const epi_model_params *prm;     // per group
   CArr epsilon;                    // [B] or absent
+  const double *eps_grid;          // sweep: shared grid, epsilon = eps_grid[(b0 + b) % eps_mod]
+  int eps_mod;
   const double *u_grp; CArr u_trj; // per group [T][L]  |  per trajectory [T][L][B]
   const double *x_grp; CArr x_trj; // per group [T]     |  per trajectory [T][B]
   int r_mode, fixed_R;
@@ -42,10 +45,12 @@ struct EkfParams {
   double v_bar, beta, gamma;
   // the forward tape (always present: caller outputs or scratch)
   TArr S_MINUS, S_PLUS, P_MINUS, P_PLUS;
+  int tape_packed;                 // 1: P_MINUS/P_PLUS scratch holds the packed upper triangle
+                                   //    ([T][m(m+1)/2][B], generic models only)
   TArr J;                          // scratch smoother gains [T-1][m*m][B]
   // optional outputs
   TArr u_opt, u_opt_smooth, S_SMOOTH, P_SMOOTH, K_GAIN, innov, rho;
-  int *status;                     // [caller B] (+b0) or null
+  int *status;                     // [B] of this wave, or null
   // sweep extras: per-day scalars consumed by the fused rollout
   TArr dot_day;                    // [T][B] gamma*a'*(u_max - u_opt_smooth(:,t))
   TArr cost_day;                   // [T][B] sum_j w(j,t)*u_opt_smooth(j,t)
@@ -62,34 +67,46 @@ void launch_eks_backward(const EkfParams &p, cudaStream_t st);
 struct SeirpParams {
   int B, K, rate_mode, saturated, out_mode;
   double dt, beta_0, beta_s, mu_0, mu_s, sigma, i_0;
-  const double *rates, *ic;
-  double *out;
+  CArr rates;                  // CONST [7][B]; SERIES [K][7][B]
+  const double *rates_shared;  // SHARED_SERIES [7][K]
+  CArr ic;                     // [5][B]
+  TArr out;                    // FULL [5][K][B]; FINAL [5][B]
 };
 void launch_seirp(const SeirpParams &p, cudaStream_t st);
 
 struct RolloutParams {
   int B, K, L, G;
+  long long b0;
   const epi_model_params *prm;
-  const double *x0, *noise_std;
+  const double *x0, *noise_std;   // per group [3]
   int u_kind;  // EPI_U_F64, EPI_U_U8, or 2 = precomputed per-day scalars (sweep)
-  const void *u;
-  const double *noise;
-  double *s, *i, *alpha;
+  const void *u; long long u_stride, u_off;   // [K][L][B]
+  CArr noise;                     // [K][3][B]
+  TArr s, i, alpha;               // [K][B]
   int T_total, T_hist;
-  const double *j0_prefix, *j1_prefix, *w;
-  const double *newcases_hist;  // sweep: per group [T_hist] (summed in-kernel)
-  const double *dot_day, *cost_day;  // sweep: [T][B]
-  double *J0, *J1;
+  const double *j0_prefix, *j1_prefix, *w;    // per group
+  const double *newcases_hist;    // sweep: per group [T_hist] (summed in-kernel)
+  CArr dot_day, cost_day;         // sweep: [T][B]
+  TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);
 
 struct SiParams {
   int B, K;
   double dt;
-  const double *alpha, *beta, *s0, *i0;
-  double *s, *i;
+  CArr alpha, beta, s0, i0;
+  TArr s, i;
 };
 void launch_si(const SiParams &p, cudaStream_t st);
+
+struct CostParams {
+  int B, T, L, G;
+  long long b0;
+  CArr newcases, inputs;    // [T][B], [T][L][B]
+  const double *weights;    // per group [T][L]
+  TArr J0, J1;
+};
+void launch_npicost(const CostParams &p, cudaStream_t st);
 
 struct ParetoParams {
   int n_sets, n;
@@ -102,5 +119,9 @@ void launch_pareto(const ParetoParams &p, cudaStream_t st);
 // gather the knee schedule: u_knee[r][t][j] = u_fore[t][j][r*n_eps + I_opt[r]]
 void launch_gather_knee(const double *u_fore, const int *I_opt, double *u_knee, int n_regions,
                         int n_eps, int Tf, int L, cudaStream_t st);
+
+// FP64 FMA throughput probe (bench.py's measured FP64 roof): each thread runs
+// `iters` rounds of 8 independent dependent-FMA chains; writes one value/thread.
+void launch_fp64_probe(double *out, int blocks, int threads, int iters, cudaStream_t st);
 
 }  // namespace epi

@@ -15,32 +15,32 @@ template <int RATE_MODE, bool SAT, bool FULL>
 __global__ void __launch_bounds__(256) seirp_kernel(const __grid_constant__ SeirpParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
-  const size_t B = (size_t)P.B;
   const int K = P.K;
-  const double dt = P.dt;
-  double S = P.ic[0 * B + b], E = P.ic[1 * B + b], I = P.ic[2 * B + b], R = P.ic[3 * B + b],
-         Pd = P.ic[4 * B + b];
-  double ae = 0, ai = 0, ka = 0, ro = 0, be = 0, mu = 0, ga = 0;
-  if (RATE_MODE == EPI_RATES_CONST) {
-    ae = P.rates[0 * B + b]; ai = P.rates[1 * B + b]; ka = P.rates[2 * B + b];
-    ro = P.rates[3 * B + b]; be = P.rates[4 * B + b]; mu = P.rates[5 * B + b];
-    ga = P.rates[6 * B + b];
-  }
-  double *__restrict__ out = P.out;
-  const size_t KB = (size_t)K * B;
   if (K <= 0) return;
+  const double dt = P.dt;
+  const size_t is = (size_t)P.ic.stride, rs = (size_t)P.rates.stride, os = (size_t)P.out.stride;
+  const double *__restrict__ ic = P.ic.p + P.ic.off + b;
+  double S = ic[0], E = ic[is], I = ic[2 * is], R = ic[3 * is], Pd = ic[4 * is];
+  double ae = 0, ai = 0, ka = 0, ro = 0, be = 0, mu = 0, ga = 0;
+  const double *__restrict__ rt = (RATE_MODE == EPI_RATES_SHARED_SERIES) ? P.rates_shared
+                                                                         : P.rates.p + P.rates.off + b;
+  if (RATE_MODE == EPI_RATES_CONST) {
+    ae = rt[0]; ai = rt[rs]; ka = rt[2 * rs]; ro = rt[3 * rs]; be = rt[4 * rs]; mu = rt[5 * rs];
+    ga = rt[6 * rs];
+  }
+  double *__restrict__ out = P.out.p + P.out.off + b;
+  const size_t KB = (size_t)K * os;  // FULL: out[f][t][b]
   if (FULL) {
-    out[0 * KB + b] = S; out[1 * KB + b] = E; out[2 * KB + b] = I; out[3 * KB + b] = R;
-    out[4 * KB + b] = Pd;  // :20-24
+    out[0 * KB] = S; out[1 * KB] = E; out[2 * KB] = I; out[3 * KB] = R; out[4 * KB] = Pd;  // :20-24
   }
   for (int t = 0; t + 1 < K; ++t) {  // :26  (only rate samples 0..K-2 are read)
     if (RATE_MODE == EPI_RATES_SHARED_SERIES) {
-      const double *r = P.rates + t;
+      const double *r = rt + t;
       ae = r[0]; ai = r[(size_t)K]; ka = r[(size_t)2 * K]; ro = r[(size_t)3 * K];
       be = r[(size_t)4 * K]; mu = r[(size_t)5 * K]; ga = r[(size_t)6 * K];
     } else if (RATE_MODE == EPI_RATES_SERIES) {
-      const double *r = P.rates + (size_t)t * 7 * B + b;
-      ae = r[0]; ai = r[B]; ka = r[2 * B]; ro = r[3 * B]; be = r[4 * B]; mu = r[5 * B]; ga = r[6 * B];
+      const double *r = rt + (size_t)t * 7 * rs;
+      ae = r[0]; ai = r[rs]; ka = r[2 * rs]; ro = r[3 * rs]; be = r[4 * rs]; mu = r[5 * rs]; ga = r[6 * rs];
     }
     if (SAT) {
       const double h = (tanh((I - P.i_0) / P.sigma) + 1.0) / 2.0;  // Saturated :27
@@ -55,14 +55,13 @@ __global__ void __launch_bounds__(256) seirp_kernel(const __grid_constant__ Seir
     const double Pn = (mu * I) * dt + Pd;
     S = Sn; E = En; I = In; R = Rn; Pd = Pn;
     if (FULL) {
-      const size_t o = (size_t)(t + 1) * B + b;
+      const size_t o = (size_t)(t + 1) * os;
       out[0 * KB + o] = S; out[1 * KB + o] = E; out[2 * KB + o] = I; out[3 * KB + o] = R;
       out[4 * KB + o] = Pd;
     }
   }
   if (!FULL) {
-    out[0 * B + b] = S; out[1 * B + b] = E; out[2 * B + b] = I; out[3 * B + b] = R;
-    out[4 * B + b] = Pd;
+    out[0] = S; out[os] = E; out[2 * os] = I; out[3 * os] = R; out[4 * os] = Pd;
   }
 }
 
@@ -93,8 +92,7 @@ template <int U_KIND>
 __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
-  const size_t B = (size_t)P.B;
-  const int g = b / P.G;
+  const long long g = (P.b0 + b) / P.G;
   const epi_model_params *__restrict__ prm = P.prm + g;
   const int K = P.K, L = P.L;
   const double dt = prm->dt, beta = prm->beta, gamma = prm->gamma, bb = prm->b;
@@ -102,25 +100,30 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   double S = P.x0[3 * g + 0], I = P.x0[3 * g + 1], A = P.x0[3 * g + 2];
   double sd_s = 0.0, sd_i = 0.0, sd_a = 0.0;
   if (P.noise_std) { sd_s = P.noise_std[3 * g + 0]; sd_i = P.noise_std[3 * g + 1]; sd_a = P.noise_std[3 * g + 2]; }
-  const bool want_cost = P.J0 != nullptr;
-  // NPICost accumulators continue the per-group history prefixes
+  const bool want_cost = P.J0.p != nullptr;
+  const size_t ds = (size_t)P.dot_day.stride, cs = (size_t)P.cost_day.stride;
+  const double *__restrict__ dotp = (U_KIND == 2) ? P.dot_day.p + P.dot_day.off + b : nullptr;
+  const double *__restrict__ costp = (U_KIND == 2 && P.cost_day.p) ? P.cost_day.p + P.cost_day.off + b : nullptr;
+  // NPICost accumulators continue over the history
   double a0 = 0.0, a1 = 0.0;
   if (want_cost) {
     if (U_KIND == 2) {
       const double *nh = P.newcases_hist + (size_t)g * P.T_hist;
       for (int t = 0; t < P.T_hist; ++t) a0 += nh[t];
-      for (int t = 0; t < P.T_hist; ++t) a1 += P.cost_day[(size_t)t * B + b];
+      for (int t = 0; t < P.T_hist; ++t) a1 += costp[(size_t)t * cs];
     } else {
       a0 = P.j0_prefix ? P.j0_prefix[g] : 0.0;
       a1 = P.j1_prefix ? P.j1_prefix[g] : 0.0;
     }
   }
   const int Th = (U_KIND == 2) ? P.T_hist : 0;
+  const size_t us = (size_t)P.u_stride, ns = (size_t)P.noise.stride;
+  const double *__restrict__ nz = P.noise.p ? P.noise.p + P.noise.off + b : nullptr;
   for (int t = 0; t < K; ++t) {  // :24-28
     double dot, cday = 0.0;
     if (U_KIND == 2) {
-      dot = P.dot_day[(size_t)(Th + t) * B + b];
-      cday = P.cost_day[(size_t)(Th + t) * B + b];
+      dot = dotp[(size_t)(Th + t) * ds];
+      if (costp) cday = costp[(size_t)(Th + t) * cs];
     } else {
       dot = 0.0;
       const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
@@ -128,8 +131,9 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       for (int j = 0; j < EPI_LMAX; ++j) {
         if (j < L) {
           double uj;
-          if (U_KIND == EPI_U_F64) uj = ((const double *)P.u)[((size_t)t * L + j) * B + b];
-          else uj = (double)((const unsigned char *)P.u)[((size_t)t * L + j) * B + b];
+          const size_t ui = ((size_t)t * L + j) * us + (size_t)P.u_off + b;
+          if (U_KIND == EPI_U_F64) uj = ((const double *)P.u)[ui];
+          else uj = (double)((const unsigned char *)P.u)[ui];
           const double gj = gamma * prm->a[j];
           const double d = prm->u_max[j] - uj;
           dot = (j == 0) ? gj * d : fma(gj, d, dot);
@@ -140,28 +144,28 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
         }
       }
     }
-    double ns = 0.0, ni = 0.0, na = 0.0;
-    if (P.noise) {
-      ns = P.noise[((size_t)t * 3 + 0) * B + b];
-      ni = P.noise[((size_t)t * 3 + 1) * B + b];
-      na = P.noise[((size_t)t * 3 + 2) * B + b];
+    double n_s = 0.0, n_i = 0.0, n_a = 0.0;
+    if (nz) {
+      n_s = nz[((size_t)t * 3 + 0) * ns];
+      n_i = nz[((size_t)t * 3 + 1) * ns];
+      n_a = nz[((size_t)t * 3 + 2) * ns];
     }
     const double asi = (A * S) * I;
-    const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + ns * sd_s)));
-    const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + ni * sd_i)));
-    const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dot) + na * sd_a)));
+    const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + n_s * sd_s)));
+    const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + n_i * sd_i)));
+    const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dot) + n_a * sd_a)));
     S = Sn; I = In; A = An;
-    if (P.s) P.s[(size_t)t * B + b] = S;
-    if (P.i) P.i[(size_t)t * B + b] = I;
-    if (P.alpha) P.alpha[(size_t)t * B + b] = A;
+    if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
+    if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
+    if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
     if (want_cost) {
       a0 += (S * I) * A;  // s.*i.*alpha (:493)
       a1 += cday;
     }
   }
   if (want_cost) {
-    P.J0[b] = a0 / (double)P.T_total;                        // NPICost.m:6
-    P.J1[b] = a1 / (double)((size_t)L * (size_t)P.T_total);  // NPICost.m:10
+    P.J0.p[P.J0.off + b] = a0 / (double)P.T_total;                        // NPICost.m:6
+    P.J1.p[P.J1.off + b] = a1 / (double)((size_t)L * (size_t)P.T_total);  // NPICost.m:10
   }
 }
 
@@ -179,23 +183,51 @@ void launch_rollout(const RolloutParams &p, cudaStream_t st) {
 __global__ void __launch_bounds__(256) si_kernel(const __grid_constant__ SiParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
-  const size_t B = (size_t)P.B;
   if (P.K <= 0) return;
-  const double dt = P.dt, beta = P.beta[b];
-  double S = P.s0[b], I = P.i0[b];
-  P.s[b] = S; P.i[b] = I;  // :15-16
+  const double dt = P.dt, beta = P.beta.p[P.beta.off + b];
+  double S = P.s0.p[P.s0.off + b], I = P.i0.p[P.i0.off + b];
+  double *__restrict__ so = P.s.p + P.s.off + b;
+  double *__restrict__ io = P.i.p + P.i.off + b;
+  const double *__restrict__ al = P.alpha.p + P.alpha.off + b;
+  so[0] = S; io[0] = I;  // :15-16
   for (int t = 0; t + 1 < P.K; ++t) {  // :19-22
-    const double A = P.alpha[(size_t)t * B + b];
+    const double A = al[(size_t)t * P.alpha.stride];
     const double Sn = mmax(0.0, mmin(1.0, S - ((dt * A) * S) * I));
     const double In = mmax(0.0, mmin(1.0, I + dt * (((A * S) * I) - beta * I)));
     S = Sn; I = In;
-    P.s[(size_t)(t + 1) * B + b] = S;
-    P.i[(size_t)(t + 1) * B + b] = I;
+    so[(size_t)(t + 1) * P.s.stride] = S;
+    io[(size_t)(t + 1) * P.i.stride] = I;
   }
 }
 void launch_si(const SiParams &p, cudaStream_t st) {
   const int block = 128;
   si_kernel<<<(p.B + block - 1) / block, block, 0, st>>>(p);
+}
+
+// ===========================================================================
+// NPICost stand-alone (Tools/NPICost.m:6-10)
+// ===========================================================================
+__global__ void __launch_bounds__(256) npicost_kernel(const __grid_constant__ CostParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const long long g = (P.b0 + b) / P.G;
+  const int T = P.T, L = P.L;
+  const double *__restrict__ nc = P.newcases.p + P.newcases.off + b;
+  const double *__restrict__ in = P.inputs.p + P.inputs.off + b;
+  const double *__restrict__ w = P.weights + (size_t)g * T * L;
+  double a0 = 0.0, a1 = 0.0;
+  for (int t = 0; t < T; ++t) {
+    a0 += nc[(size_t)t * P.newcases.stride];
+    double c = w[(size_t)t * L] * in[((size_t)t * L) * P.inputs.stride];
+    for (int j = 1; j < L; ++j) c = c + w[(size_t)t * L + j] * in[((size_t)t * L + j) * P.inputs.stride];
+    a1 += c;
+  }
+  P.J0.p[P.J0.off + b] = a0 / (double)T;                        // :6
+  P.J1.p[P.J1.off + b] = a1 / (double)((size_t)L * (size_t)T);  // :9-10
+}
+void launch_npicost(const CostParams &p, cudaStream_t st) {
+  const int block = 128;
+  npicost_kernel<<<(p.B + block - 1) / block, block, 0, st>>>(p);
 }
 
 // ===========================================================================
@@ -285,6 +317,25 @@ void launch_gather_knee(const double *u_fore, const int *I_opt, double *u_knee, 
   if (!total) return;
   gather_knee_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(u_fore, I_opt, u_knee,
                                                                      n_regions, n_eps, Tf * L);
+}
+
+// ===========================================================================
+// FP64 FMA throughput probe (measured FP64 roof for bench.py's roofline)
+// ===========================================================================
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters) {
+  const double x = 1.0 + 1e-9 * (double)threadIdx.x, y = 1e-12 * (double)(blockIdx.x + 1);
+  double a0 = 0.1, a1 = 0.2, a2 = 0.3, a3 = 0.4, a4 = 0.5, a5 = 0.6, a6 = 0.7, a7 = 0.8;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+      a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+void launch_fp64_probe(double *out, int blocks, int threads, int iters, cudaStream_t st) {
+  fp64_probe_kernel<<<blocks, threads, 0, st>>>(out, iters);
 }
 
 }  // namespace epi

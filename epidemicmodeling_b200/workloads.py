@@ -1,0 +1,130 @@
+"""Host-side drivers that batch the reference's sweep loops onto the engine.
+
+These mirror the loop bodies of Tools/TrainPredictPrescribeNPI.m:370-392 (the
+3-state "fixed input" EKF/EKS that supplies the historic estimate and the rollout
+start) and :415-495,624-633 (the epsilon sweep + Pareto step), turning the
+region x epsilon loops into one batch.  Input construction is numpy glue; every
+filter / smoother / rollout / cost / Pareto computation runs in libepi_b200.so.
+"""
+import numpy as np
+
+from . import _capi as K
+from .engine import pack_params
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _cm(P):
+    """m x m matrix -> column-major flat (symmetric matrices are unchanged)."""
+    return np.ascontiguousarray(np.asarray(P, dtype=np.float64).T).ravel()
+
+
+def fixed_input_batch(inputs):
+    """Arrays of the 3-state fixed-input EKF/EKS (one trajectory per region)."""
+    L = inputs[0]["u_fixed"].shape[0]
+    return dict(
+        prm=pack_params([r["setup3"]["params"] for r in inputs], L),
+        u=np.stack([np.ascontiguousarray(r["u_fixed"].T) for r in inputs]),     # [nR,T,L]
+        x=np.stack([r["x"] for r in inputs]),                                    # [nR,T]
+        R=np.stack([r["R_v"] for r in inputs]),                                  # [nR,T]
+        Q=np.stack([_cm(r["setup3"]["Q_w"]) for r in inputs]),
+        s_init=np.stack([r["setup3"]["s_init"] for r in inputs]),
+        Ps_init=np.stack([_cm(r["setup3"]["Ps_init"]) for r in inputs]),
+        s_final=np.stack([r["setup3"]["s_final"] for r in inputs]),
+        Ps_final=np.stack([_cm(r["setup3"]["Ps_final"]) for r in inputs]),
+        T=inputs[0]["T"], L=L, n_regions=len(inputs),
+        beta=inputs[0]["setup3"]["beta_ekf"], gamma=inputs[0]["setup3"]["gamma_ekf"],
+        W=inputs[0]["setup3"]["W"])
+
+
+def run_fixed_input(engine, inputs):
+    """S_SMOOTH [T,3,nR] of the fixed-input round (TrainPredictPrescribeNPI.m:377)."""
+    b = fixed_input_batch(inputs)
+    out = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], b["x"], b["R"], b["Q"], b["s_init"],
+                         b["Ps_init"], b["s_final"], b["Ps_final"], B=b["n_regions"], T=b["T"],
+                         L=b["L"], G=1, r_mode=K.R_PERDAY, fixed_R=False, q_mode=K.Q_CONST,
+                         beta=b["beta"], gamma=b["gamma"], W=b["W"], order=1, outputs=("S_SMOOTH",))
+    return out["S_SMOOTH"]
+
+
+def sweep_batch(inputs, S_SMOOTH_fixed):
+    """Per-region arrays of Engine.sweep from the synthetic inputs and the
+    fixed-input smoothed states [T,3,nR] (:380-382 historic estimates, :481 start)."""
+    L = inputs[0]["u_hist"].shape[0]
+    T, Th = inputs[0]["T"], inputs[0]["T_hist"]
+    S = np.asarray(S_SMOOTH_fixed)
+    hist = S[:Th]                                             # [Th,3,nR]
+    newcases_hist = ((hist[:, 0] * hist[:, 1]) * hist[:, 2]).T  # s.*i.*alpha  [nR,Th]
+    x0 = hist[Th - 1].T                                       # [nR,3]
+    u = np.stack([np.concatenate([np.ascontiguousarray(r["u_hist"].T), np.full((T - Th, L), np.nan)])
+                  for r in inputs])                           # :458
+    return dict(
+        prm=pack_params([r["setup6"]["params"] for r in inputs], L),
+        u=u, x=np.stack([r["x"] for r in inputs]), R=np.stack([r["R_v"] for r in inputs]),
+        s_init=np.stack([r["setup6"]["s_init"] for r in inputs]),
+        Ps_init=np.stack([_cm(r["setup6"]["Ps_init"]) for r in inputs]),
+        s_final=np.stack([r["setup6"]["s_final"] for r in inputs]),
+        Ps_final=np.stack([_cm(r["setup6"]["Ps_final"]) for r in inputs]),
+        Q=np.stack([_cm(r["setup6"]["Q_w"]) for r in inputs]),
+        x0=np.ascontiguousarray(x0), newcases_hist=np.ascontiguousarray(newcases_hist),
+        weights=np.stack([np.ascontiguousarray(r["weights"].T) for r in inputs]),  # [nR,T,L]
+        n_regions=len(inputs), T=T, T_hist=Th, L=L,
+        beta_ekf=inputs[0]["setup6"]["beta_ekf"], gamma_ekf=inputs[0]["setup6"]["gamma_ekf"],
+        W=inputs[0]["setup6"]["W"])
+
+
+_SWEEP_ARRAYS = ("u", "x", "R", "s_init", "Ps_init", "s_final", "Ps_final", "Q", "x0",
+                 "newcases_hist", "weights")
+
+
+def sweep_to_device(batch, eps, device):
+    """Upload a sweep batch once (bench `value` leg: inputs resident in HBM)."""
+    from .engine import params_to_device
+    d = dict(batch)
+    for k in _SWEEP_ARRAYS:
+        d[k] = torch.from_numpy(np.ascontiguousarray(batch[k])).to(device)
+    d["prm"] = params_to_device(batch["prm"], device)
+    d["eps"] = torch.from_numpy(np.ascontiguousarray(eps, dtype=np.float64)).to(device)
+    return d
+
+
+def run_sweep(engine, batch, eps, **kw):
+    """One pass of the fused sweep; `batch` from sweep_batch() (host) or sweep_to_device()."""
+    e = batch.get("eps", eps)
+    return engine.sweep(batch["prm"], e, batch["u"], batch["x"], batch["R"], batch["s_init"],
+                        batch["Ps_init"], batch["s_final"], batch["Ps_final"], batch["Q"],
+                        batch["x0"], batch["newcases_hist"], batch["weights"],
+                        n_regions=batch["n_regions"], T=batch["T"], T_hist=batch["T_hist"],
+                        L=batch["L"], beta_ekf=batch["beta_ekf"], gamma_ekf=batch["gamma_ekf"],
+                        W=batch["W"], **kw)
+
+
+def shard_regions(n_regions, world_size, rank):
+    """Contiguous blocks of ceil(n/G) regions per rank."""
+    per = (n_regions + world_size - 1) // world_size
+    lo = min(n_regions, rank * per)
+    return lo, min(n_regions, lo + per)
+
+
+def gather_costs(J0, J1, group=None):
+    """The path's one collective: all-gather of the per-shard (J0, J1) arrays.
+    J0, J1 [n_local_regions, n_eps] torch tensors (CUDA -> NCCL over NVLink; CPU -> gloo).
+    Shards may be ragged (last rank), so sizes are exchanged first."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    n_eps = J0.shape[1]
+    sizes = [torch.zeros(1, dtype=torch.int64, device=J0.device) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([J0.shape[0]], dtype=torch.int64, device=J0.device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    send = torch.zeros((2, mx, n_eps), dtype=J0.dtype, device=J0.device)
+    send[0, :J0.shape[0]] = J0
+    send[1, :J1.shape[0]] = J1
+    recv = torch.empty((ws, 2, mx, n_eps), dtype=J0.dtype, device=J0.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)  # flat: gloo and nccl agree
+    g0 = torch.cat([recv[r, 0, :sizes[r]] for r in range(ws)])
+    g1 = torch.cat([recv[r, 1, :sizes[r]] for r in range(ws)])
+    return g0, g1

@@ -98,6 +98,9 @@ long long epi_launch_count(const epi_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) of the kernels of the
  * most recent batched call, by phase; returns the number of phases written. */
 int epi_last_kernel_times(epi_ctx *ctx, float *ms, const char **names, int max);
+/* measured FP64 FMA throughput of the device (TFLOP/s): the FP64 roof that
+ * bench.py's roofline uses (MEASURED_PEAKS.json carries no FP64 figure). */
+int epi_fp64_probe(epi_ctx *ctx, int iters, double *tflops);
 
 /* SEIRP ensembles ------------------------------------------------------------
  * replaces  [s,e,i,r,p] = SEIRP(alpha_e, alpha_i, kappa, rho, beta, mu, gamma,
@@ -147,6 +150,18 @@ typedef struct {
   double *J0, *J1;             /* [B] */
 } epi_rollout_args;
 int epi_rollout_cost_batch(epi_ctx *ctx, const epi_rollout_args *a);
+
+/* replaces  [J0,J1] = NPICost(newcases, inputs, weights)          Tools/NPICost.m:1
+ * as a stand-alone call (the rollout above fuses it).  newcases [T][B],
+ * inputs [T][L][B], weights per group [T][L]; J0, J1 [B].  Summation order:
+ * per-day sums over the L inputs in row order, then over days. */
+typedef struct {
+  int mem;
+  int B, T, L, G;
+  const double *newcases, *inputs, *weights;
+  double *J0, *J1;
+} epi_npicost_args;
+int epi_npicost_batch(epi_ctx *ctx, const epi_npicost_args *a);
 
 /* replaces  [s,i] = SI_Controlled(alpha, beta, s0, i0, K, dt)   Tools/SI_Controlled.m:1
  * alpha [K][B]; beta, s0, i0 per trajectory [B]; outputs s, i [K][B]. */

@@ -1,0 +1,161 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and
+exports every symbol include/epi_b200.h declares; the ctypes structs match the C
+layout; without a GPU the product path FAILS LOUDLY (no CPU fallback); the
+host-side sharding/gather logic works at world_size 2 over gloo."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from epidemicmodeling_b200 import _build, _capi
+    _build.build()
+    return _capi.load()
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "epi_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(epi_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from epidemicmodeling_b200 import _capi
+    declared = _declared_symbols()
+    assert len(declared) >= 16
+    for name in declared:
+        assert hasattr(lib, name), f"libepi_b200.so lacks {name}"
+    assert sorted(_capi.SYMBOLS) == declared  # the binding covers the header exactly
+
+
+def test_ctypes_structs_match_c_layout(lib, tmp_path):
+    """Compile a tiny C program against the header and compare sizeof/offsetof."""
+    from epidemicmodeling_b200 import _capi as K
+    probes = {
+        "epi_model_params": (K.ModelParams, ["dt", "a", "w", "L", "obs_type"]),
+        "epi_seirp_args": (K.SeirpArgs, ["rates", "saturated", "i_0", "out"]),
+        "epi_rollout_args": (K.RolloutArgs, ["prm", "u_kind", "u", "T_total", "J1"]),
+        "epi_npicost_args": (K.NpiCostArgs, ["newcases", "J1"]),
+        "epi_si_args": (K.SiArgs, ["dt", "alpha", "i"]),
+        "epi_ekf_args": (K.EkfArgs, ["prm", "u", "R", "Q", "v_bar", "W", "u_opt", "rho", "status"]),
+        "epi_pareto_args": (K.ParetoArgs, ["J0", "I_opt"]),
+        "epi_sweep_args": (K.SweepArgs, ["prm", "beta_ekf", "W", "x0", "noise", "J0", "P_first"]),
+    }
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "epi_b200.h"', "int main(){"]
+    for cname, (_, fields) in probes.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append("return 0;}")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, (st, fields) in probes.items():
+        assert int(got[cname]) == C.sizeof(st), cname
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(st, f).offset, (cname, f)
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from epidemicmodeling_b200 import _capi as K
+    h = C.c_void_p()
+    rc = lib.epi_create(0, C.byref(h))
+    assert rc == K.ERR_NO_DEVICE and not h.value
+    assert b"no CPU fallback" in lib.epi_last_error(None)
+    from epidemicmodeling_b200 import api
+    with pytest.raises(K.EpiError):
+        api.SEIRP(0.65, 0.005, 0.05, 0.08, 0.1, 0.02, 0.0, 1 - 1e-6, 1e-6, 0, 0, 0, 50, 0.1)
+
+
+def test_product_package_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "epidemicmodeling_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "epi_oracle" not in txt, f
+    for f in os.listdir(os.path.join(ROOT, "matlab")):
+        assert "oracle" not in open(os.path.join(ROOT, "matlab", f), errors="ignore").read(), f
+
+
+def test_pack_params_and_qr_dispatch():
+    from epidemicmodeling_b200 import api
+    from epidemicmodeling_b200 import _capi as K
+    from epidemicmodeling_b200.engine import pack_params
+    p = pack_params([dict(dt=1.0, beta=0.2, gamma=0.1, b=0.05, alpha_min=1e-8, alpha_max=100.0,
+                          a=np.arange(12.0), u_max=np.ones(12), w=np.arange(24.0).reshape(12, 2),
+                          obs_type="TOTALCASES")], 12)
+    assert p[0].L == 12 and p[0].obs_type == K.OBS_TOTALCASES
+    assert list(p[0].w) == list(np.arange(0, 24, 2.0))      # a 12xT `w` keeps column 1 only
+    with pytest.raises(ValueError, match="unknown observation type"):
+        pack_params([dict(obs_type="DEATHS")], 12)
+    T, m = 40, 3
+    q, Qf, r, fixed, Rf = api._classify_QR(np.eye(3) * 2.0, np.ones((1, T)), T, m)
+    assert (q, r, fixed) == (K.Q_CONST, K.R_PERDAY, 0) and Qf.size == 9 and Rf.size == T
+    q, Qf, r, fixed, Rf = api._classify_QR(np.ones(T), np.array([[0.5]]), T, m)
+    assert (q, r, fixed) == (K.Q_PERDAY_SCALAR, K.R_CONST, 1)
+    q, Qf, r, fixed, Rf = api._classify_QR(np.ones((3, 3, T)), np.ones((1, 1, T)), T, m)
+    assert (q, r, fixed) == (K.Q_PERDAY_FULL, K.R_PERDAY, 1)  # square pages => fixed_R stays true (:79-81)
+    with pytest.raises(ValueError, match="Process noise"):
+        api._classify_QR(np.ones(7), np.array([[0.5]]), T, m)
+    with pytest.raises(ValueError, match="Observation noise"):
+        api._classify_QR(np.eye(3), np.ones(7), T, m)
+
+
+def test_shard_regions_covers_everything():
+    from epidemicmodeling_b200.workloads import shard_regions
+    for n in (1, 7, 236):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_regions(n, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+
+
+_GLOO_SCRIPT = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import torch, torch.distributed as dist
+    from epidemicmodeling_b200.workloads import shard_regions, gather_costs
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    rank, n, ne = dist.get_rank(), 7, 5            # ragged: 4 + 3 regions
+    full0 = torch.arange(n * ne, dtype=torch.float64).reshape(n, ne)
+    full1 = -full0
+    lo, hi = shard_regions(n, 2, rank)
+    g0, g1 = gather_costs(full0[lo:hi].clone(), full1[lo:hi].clone())
+    assert torch.equal(g0, full0) and torch.equal(g1, full1), (rank, g0)
+    dist.barrier()
+    dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+def test_gather_costs_world_size_2_gloo(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "gloo_gather.py"
+    script.write_text(_GLOO_SCRIPT.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

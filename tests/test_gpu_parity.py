@@ -1,0 +1,448 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the
+same seeded inputs and against the committed golden vectors.
+
+Bar (BASELINE.md 4 / north_star): FP64 rel <= 1e-9 for SEIRP/EKF states, <= 1e-6 for
+converged optimal-control costs and schedules.  Because the kernels and the oracle
+execute the same IEEE-754 operation sequence (DESIGN.md "Arithmetic contract"), the
+tests assert the much stronger BIT-EXACT agreement wherever no libm call is involved
+(everything except SEIRPSaturatedResource's tanh, held to 1e-12).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from epidemicmodeling_b200 import _capi as K
+from epidemicmodeling_b200 import api, synthetic as syn, workloads as wl
+from epidemicmodeling_b200.engine import pack_params
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EKF_KEYS = ("u_opt", "u_opt_smooth", "S_MINUS", "S_PLUS", "S_SMOOTH", "P_MINUS", "P_PLUS", "P_SMOOTH",
+            "K_GAIN", "innovations", "rho")
+TOL_STATE = 1e-9   # north_star tolerance for SEIRP / EKF states
+TOL_COST = 1e-6    # north_star tolerance for optimal-control costs and schedules
+
+
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def ekf_args(c):
+    return (c["u"], c["x"], c["params"], c["s_init"], c["Ps_init"], c["s_final"], c["Ps_final"],
+            c["w_bar"], c["v_bar"], c["Q_w"], c["R_v"], c["beta"], c["gamma"], c["inv_monitor_len"],
+            c["order"])
+
+
+def assert_bits(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b, equal_nan=True):
+        bad = np.flatnonzero(~((a == b) | (np.isnan(a) & np.isnan(b))).ravel())
+        k = bad[0]
+        raise AssertionError(f"{what}: {bad.size}/{a.size} entries differ; first at flat {k}: "
+                             f"gpu={a.ravel()[k]!r} oracle={b.ravel()[k]!r}")
+
+
+# ------------------------------------------------------------------------------ SEIRP
+@pytest.mark.parametrize("name", ["A", "B", "C", "D", "E", "Q", "Y"])
+def test_seirp_signature_bit_exact(engine, name):
+    kw = cases.seirp_scenarios()[name]
+    got = api.SEIRP(**kw)
+    want = orc().SEIRP(**kw)
+    g = np.load(os.path.join(GOLD, "seirp.npz"))
+    for a, b in zip(got, want):
+        assert_bits(a, b, f"SEIRP {name}")
+        assert np.max(np.abs(a - b) / (np.abs(b) + 1e-300)) <= TOL_STATE
+    assert_bits(np.array([o[0, -1] for o in got]), g[f"{name}_last"], f"golden {name}")
+    if name in ("A", "Y"):
+        assert_bits(np.concatenate(got), g[f"{name}_full"], f"golden full {name}")
+
+
+def test_seirp_saturated_tolerance(engine):
+    kw = cases.seirp_saturated_case()
+    got = api.SEIRPSaturatedResource(**kw)
+    want = orc().SEIRPSaturatedResource(**kw)
+    for a, b in zip(got, want):
+        # tanh is not correctly rounded on either side: tolerance parity
+        assert np.max(np.abs(a - b) / (np.abs(b) + 1e-30)) < 1e-12
+    g = np.load(os.path.join(GOLD, "seirp.npz"))
+    assert np.max(np.abs(np.concatenate(got)[:, ::100] - g["SAT_every100"]) / (np.abs(g["SAT_every100"]) + 1e-30)) < 1e-12
+
+
+@pytest.mark.parametrize("rate_mode", ["const", "series"])
+def test_seirp_ensemble_bit_exact(engine, rate_mode):
+    B, Kn = 3000, 97  # ragged: not a multiple of the block size
+    rates, ic = syn.seirp_ensemble(B, seed=7)
+    if rate_mode == "const":
+        out = engine.seirp(rates, ic, Kn, 1.0)
+        fin = engine.seirp(rates, ic, Kn, 1.0, out_mode=K.SEIRP_OUT_FINAL)
+        rser = None
+    else:
+        rng = np.random.default_rng(8)
+        rser = rates[None] * (1.0 + 0.1 * rng.random((Kn, 7, B)))
+        out = engine.seirp(rser, ic, Kn, 1.0, rate_mode=K.RATES_SERIES)
+        fin = engine.seirp(rser, ic, Kn, 1.0, rate_mode=K.RATES_SERIES, out_mode=K.SEIRP_OUT_FINAL)
+    assert_bits(fin, out[:, -1, :], "final-only mode")
+    o = orc()
+    for b in list(range(0, B, 211)) + [B - 1]:
+        r = [rates[f, b] if rser is None else rser[:, f, b] for f in range(7)]
+        want = o.SEIRP(*r, *ic[:, b], Kn * 1.0, 1.0)
+        for f in range(5):
+            assert_bits(out[f, :, b], want[f][0], f"ensemble b={b} f={f}")
+
+
+def test_seirp_edge_cases(engine):
+    rates, ic = syn.seirp_ensemble(5, seed=1)
+    out = engine.seirp(rates, ic, 1, 1.0)                   # K = 1: only the initial condition
+    assert_bits(out[:, 0, :], ic)
+    assert engine.seirp(rates[:, :0], ic[:, :0], 10, 1.0).shape == (5, 10, 0)   # empty batch
+
+
+# ------------------------------------------------------------------------------ rollout / cost / Pareto
+@pytest.mark.parametrize("noisy", [False, True])
+def test_sialpha_controlled_signature(engine, noisy):
+    rc = cases.rollout_case(noisy=noisy)
+    got = api.SIalpha_Controlled(**{("K_" if k == "K" else k): v for k, v in rc.items()})
+    want = orc().SIalpha_Controlled(**rc)
+    for a, b in zip(got, want):
+        assert_bits(a, b, "SIalpha_Controlled")
+    if noisy:
+        g = np.load(os.path.join(GOLD, "rollout.npz"))
+        assert_bits(got[0], g["s"]); assert_bits(got[1], g["i"]); assert_bits(got[2], g["alpha"])
+
+
+@pytest.mark.parametrize("u_kind", ["f64", "u8"])
+def test_rollout_cost_batch(engine, u_kind):
+    """BASELINE config 5 shape, small: regions x random schedules x 45 days with NPICost fused."""
+    nR, nS, Kn, L = 3, 257, 45, 12
+    reg = syn.load_regions(nR)
+    rng = np.random.default_rng(21)
+    B = nR * nS
+    u = np.stack([syn.random_schedules(nS, Kn, reg["npi_max"], rng) for _ in range(nR)])  # [nR,nS,L,K]
+    u_kb = np.ascontiguousarray(np.transpose(u, (3, 2, 0, 1)).reshape(Kn, L, B))
+    noise = rng.standard_normal((Kn, 3, B))
+    prm_d = [dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                  alpha_min=1e-8, alpha_max=100.0) for r in range(nR)]
+    x0 = np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)])
+    nstd = np.array([[100 / reg["N"][r], 300 / reg["N"][r], 1e-2] for r in range(nR)])
+    w = np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)])  # [nR,K,L]
+    Th = 30
+    j0p, j1p = rng.random(nR), rng.random(nR) * 10
+    uin = u_kb.astype(np.uint8) if u_kind == "u8" else u_kb
+    res = engine.rollout_cost(pack_params(prm_d, L), x0, uin, Kn, L, G=nS, noise_std=nstd, noise=noise,
+                              want_traj=True, want_cost=True, T_total=Th + Kn, j0_prefix=j0p,
+                              j1_prefix=j1p, w=w)
+    o = orc()
+    for b in list(range(0, B, 97)) + [B - 1]:
+        r = b // nS
+        s, i, al = o.SIalpha_Controlled(u_kb[:, :, b].T, *x0[r], reg["npi_max"], 1e-8, 100.0, syn.GAMMA,
+                                        reg["a"][r], reg["b"][r], syn.BETA, *nstd[r], Kn, 1.0,
+                                        noise=noise[:, :, b].T)
+        assert_bits(res["s"][:, b], s[0]); assert_bits(res["i"][:, b], i[0]); assert_bits(res["alpha"][:, b], al[0])
+        nc = (s * i) * al
+        a0, a1 = j0p[r], j1p[r]
+        for t in range(Kn):
+            a0 += nc[0, t]
+            c = w[r, t, 0] * u_kb[t, 0, b]
+            for j in range(1, L):
+                c = c + w[r, t, j] * u_kb[t, j, b]
+            a1 += c
+        assert res["J0"][b] == a0 / (Th + Kn) and res["J1"][b] == a1 / (L * (Th + Kn))
+
+
+def test_si_controlled_and_npicost_signatures(engine):
+    al = 0.2 + 0.1 * np.sin(np.arange(50) / 5.0)
+    got = api.SI_Controlled(al, 0.2, 0.999, 0.001, 50, 1.0)
+    want = orc().SI_Controlled(al, 0.2, 0.999, 0.001, 50, 1.0)
+    assert_bits(got[0], want[0]); assert_bits(got[1], want[1])
+    rng = np.random.default_rng(0)
+    nc, u, w = rng.random(37), rng.integers(0, 4, (12, 37)).astype(float), rng.random((12, 37))
+    assert api.NPICost(nc, u, w) == orc().NPICost(nc, u, w)
+
+
+def test_pareto_front(engine):
+    g = np.load(os.path.join(GOLD, "rollout.npz"))
+    mask, iopt = api.ParetoFront(g["pj0"], g["pj1"])
+    assert np.array_equal(mask, g["mask"]) and iopt == int(g["iopt"]) + 1
+    rng = np.random.default_rng(9)
+    J0, J1 = rng.random((17, 1000)), rng.random((17, 1000))
+    J0[:, 5] = J0[:, 2]; J1[:, 5] = J1[:, 2]           # ties
+    J0[3, 0] = np.nan                                   # NaN never dominates, skipped by the knee
+    J0[4] = 1.0; J1[4] = 2.0                            # all points identical: everything survives
+    m, io = engine.pareto(J0, J1)
+    o = orc()
+    for r in range(17):
+        wm, wi = o.pareto(J0[r], J1[r])
+        assert np.array_equal(m[r].astype(bool), wm) and io[r] == wi, r
+    # idempotence at a size the O(n^2) oracle would not like: front(front) == front
+    J0b, J1b = rng.random((1, 12000)), rng.random((1, 12000))
+    mb, _ = engine.pareto(J0b, J1b)
+    keep = mb[0].astype(bool)
+    m2, _ = engine.pareto(J0b[:, keep], J1b[:, keep])
+    assert m2.all() and keep.sum() < 100
+
+
+# ------------------------------------------------------------------------------ EKF / EKS (signatures)
+_SIGS = {
+    "ekf3_perday": (api.SIAlphaModelEKF, lambda: cases.ekf3_case(0, variant="perday"), 0),
+    "ekf3_adaptive": (api.SIAlphaModelEKF, lambda: cases.ekf3_case(1, variant="adaptive"), 0),
+    "ekf3_totalcases": (api.SIAlphaModelEKF, lambda: cases.ekf3_case(2, variant="totalcases"), 0),
+    "ekf3_endpoint": (api.SIAlphaModelEKF, lambda: cases.ekf3_case(3, variant="endpoint"), 0),
+    "ekf3_flipped": (api.SIAlphaModelBackwardEKF, lambda: cases.ekf3_case(4, variant="backward"), 1),
+    "ekf6_optctrl": (api.SIAlphaModelEKFOptControlled, lambda: cases.ekf6_case(0), 2),
+    "ekf6_flipped": (api.SIAlphaModelBackwardEKFOptControlled, lambda: cases.ekf6_case(1, backward=True), 3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_SIGS))
+def test_ekf_signatures_bit_exact(engine, name):
+    fn, mk, model = _SIGS[name]
+    c = mk()
+    got = dict(zip(EKF_KEYS, fn(*ekf_args(c))))
+    want = orc().ekf_eks(model, *ekf_args(c))
+    g = np.load(os.path.join(GOLD, f"{name}.npz"))
+    for k in EKF_KEYS:
+        assert_bits(got[k], want[k], f"{name}.{k} vs oracle")
+        assert_bits(got[k], g[k], f"{name}.{k} vs golden")
+
+
+@pytest.mark.parametrize("variant", ["tools", "codegen"])
+def test_legacy_estimator_bit_exact(engine, variant):
+    c = cases.legacy_case(0 if variant == "tools" else 1)
+    got = api.NewCaseEKFEstimatorWithOptimalNPI(*ekf_args(c), variant=variant)
+    o = orc()
+    want = o.ekf_eks(o.LEGACY_TOOLS if variant == "tools" else o.LEGACY_CODEGEN, *ekf_args(c))
+    order = ("u_opt", "S_MINUS", "S_PLUS", "S_SMOOTH", "P_MINUS", "P_PLUS", "P_SMOOTH", "K_GAIN",
+             "innovations", "rho") if variant == "tools" else \
+            ("u_opt", "S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH",
+             "innovations", "rho")
+    g = np.load(os.path.join(GOLD, f"legacy_{variant}.npz"))
+    assert len(got) == 10
+    for k, a in zip(order, got):
+        assert_bits(a, want[k], f"legacy {variant}.{k}")
+        assert_bits(a, g[k], f"legacy {variant}.{k} golden")
+
+
+def test_generic_filter_entry_and_errors(engine):
+    c = cases.ekf3_case(0)
+    a = ekf_args(c)
+    got = api.GenericExtendedKalmanFilter(a[0], a[1], api.HANDLES_SIALPHA, *a[2:])
+    want = api.SIAlphaModelEKF(*a)
+    for x, y in zip(got, want):
+        assert_bits(x, y)
+    with pytest.raises(NotImplementedError):
+        api.GenericExtendedKalmanFilter(a[0], a[1], object(), *a[2:])
+    bad = list(a); bad[-1] = 3
+    with pytest.raises(ValueError, match="Undefined order"):
+        api.SIAlphaModelEKF(*bad)
+    bad = list(a); bad[10] = np.ones(7)
+    with pytest.raises(ValueError, match="Observation noise"):
+        api.SIAlphaModelEKF(*bad)
+    bad = list(a); bad[2] = dict(c["params"], obs_type="DEATHS")
+    with pytest.raises(ValueError, match="unknown observation type"):
+        api.SIAlphaModelEKF(*bad)
+    # the C ABI itself reports the reference's errors as status codes
+    prm = pack_params([c["params"]], 12)
+    with pytest.raises(K.EpiError) as ei:
+        engine.ekf_eks(K.MODEL_SIALPHA, prm, c["u"].T.copy(), c["x"], c["R_v"], np.eye(3).ravel(),
+                       c["s_init"], np.eye(3).ravel(), c["s_final"], np.full(9, np.nan), B=1,
+                       T=c["u"].shape[1], L=12, r_mode=K.R_PERDAY, order=7)
+    assert ei.value.code == K.ERR_ORDER
+    prm[0].obs_type = 5
+    with pytest.raises(K.EpiError) as ei:
+        engine.ekf_eks(K.MODEL_SIALPHA, prm, c["u"].T.copy(), c["x"], c["R_v"], np.eye(3).ravel(),
+                       c["s_init"], np.eye(3).ravel(), c["s_final"], np.full(9, np.nan), B=1,
+                       T=c["u"].shape[1], L=12, r_mode=K.R_PERDAY)
+    assert ei.value.code == K.ERR_OBS_TYPE
+
+
+# ------------------------------------------------------------------------------ EKF / EKS (batches)
+def _ekf3_replicate_batch(nR=4, nRep=33, T_hist=70, T_fore=20, seed=31):
+    """BASELINE config 3 shape, small: regions x noise replicates with per-trajectory x."""
+    inp = syn.sweep_inputs(n_regions=nR, T_hist=T_hist, T_fore=T_fore)
+    b = wl.fixed_input_batch(inp)
+    T = b["T"]
+    rng = np.random.default_rng(seed)
+    B = nR * nRep
+    x = np.empty((T, B))
+    for r in range(nR):
+        clean = np.nan_to_num(inp[r]["x"])
+        for k in range(nRep):
+            xr = np.maximum(0.0, clean * (1.0 + 0.05 * rng.standard_normal(T)))
+            xr[np.isnan(inp[r]["x"])] = np.nan
+            xr[rng.integers(0, T_hist, 3)] = np.nan        # a few missing observations inside the history
+            x[:, r * nRep + k] = xr
+    return inp, b, x, nRep
+
+
+def test_ekf3_replicate_batch_bit_exact_and_waves(engine):
+    inp, b, x, nRep = _ekf3_replicate_batch()
+    B, T, L = x.shape[1], b["T"], b["L"]
+    kw = dict(B=B, T=T, L=L, G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False,
+              beta=b["beta"], gamma=b["gamma"], W=b["W"], want_status=True)
+    out = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"],
+                         b["s_final"], b["Ps_final"], **kw)
+    o = orc()
+    for bb in list(range(0, B, 17)) + [B - 1]:
+        r = inp[bb // nRep]
+        s3 = r["setup3"]
+        want = o.ekf_eks(o.SIALPHA, r["u_fixed"], x[:, bb], s3["params"], s3["s_init"], s3["Ps_init"],
+                         s3["s_final"], s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], r["R_v"], 1.0,
+                         s3["gamma_ekf"], s3["W"], 1)
+        assert_bits(out["S_SMOOTH"][:, :, bb].T, want["S_SMOOTH"], f"b={bb} S_SMOOTH")
+        assert_bits(out["P_SMOOTH"][:, :, bb].reshape(T, 3, 3).transpose(2, 1, 0), want["P_SMOOTH"], f"b={bb} P_SMOOTH")
+        assert_bits(out["K_GAIN"][:, :, bb].T, want["K_GAIN"][:, 0, :], f"b={bb} K")
+        assert_bits(out["rho"][:, bb], want["rho"][:, 0], f"b={bb} rho")
+        assert_bits(out["u_opt_smooth"][:, :, bb].T, want["u_opt_smooth"])
+    assert not out["status"].any()                           # full rank, no NaN/Inf guard hit
+    # lean call (tape in packed scratch) in small waves must give the same bits
+    engine.set_scratch_limit(40 * (T * 8 * 40))
+    try:
+        lean = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"],
+                              b["Ps_init"], b["s_final"], b["Ps_final"], outputs=("S_SMOOTH", "P_SMOOTH"),
+                              **kw)
+    finally:
+        engine.set_scratch_limit(0)
+    assert_bits(lean["S_SMOOTH"], out["S_SMOOTH"], "waves/packed S_SMOOTH")
+    assert_bits(lean["P_SMOOTH"], out["P_SMOOTH"], "waves/packed P_SMOOTH")
+
+
+def test_ekf3_device_memory_mode_matches_host_mode(engine):
+    import torch
+    inp, b, x, nRep = _ekf3_replicate_batch(nR=2, nRep=40)
+    B, T, L = x.shape[1], b["T"], b["L"]
+    kw = dict(B=B, T=T, L=L, G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False,
+              beta=b["beta"], gamma=b["gamma"], W=b["W"], outputs=("S_SMOOTH", "u_opt_smooth", "rho"))
+    host = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"],
+                          b["s_final"], b["Ps_final"], **kw)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    d = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], dev(b["u"]), dev(x), dev(b["R"]), dev(b["Q"]),
+                       dev(b["s_init"]), dev(b["Ps_init"]), dev(b["s_final"]), dev(b["Ps_final"]), **kw)
+    engine.sync()
+    for k in host:
+        assert_bits(d[k].cpu().numpy(), host[k], f"device-mode {k}")
+
+
+def test_ekf6_per_trajectory_epsilon_batch(engine):
+    """Generic batched entry with the 6-state model: one region, epsilon per trajectory."""
+    c = cases.ekf6_case(2, T_hist=50, T_fore=25)
+    eps = np.array([1e-9, 1e-3, 0.05, 0.3, 0.7, 0.999])
+    T, L = c["u"].shape[1], 12
+    cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+    out = engine.ekf_eks(K.MODEL_OPTCTRL, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], c["R_v"],
+                         cm(c["Q_w"]), c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]),
+                         B=eps.size, T=T, L=L, G=eps.size, epsilon=eps, r_mode=K.R_PERDAY, fixed_R=False,
+                         beta=1.0, gamma=0.995, W=21, want_status=True)
+    o = orc()
+    for e, ev in enumerate(eps):
+        cc = dict(c, params=dict(c["params"], epsilon=ev))
+        want = o.ekf_eks(o.OPTCTRL, *ekf_args(cc))
+        for k in ("S_SMOOTH", "u_opt", "u_opt_smooth", "S_PLUS"):
+            assert_bits(out[k][:, :, e].T, want[k], f"eps={ev} {k}")
+        assert_bits(out["P_SMOOTH"][:, :, e].reshape(T, 6, 6).transpose(2, 1, 0), want["P_SMOOTH"])
+        # north_star tolerance for schedules is implied by bit equality; state it anyway
+        assert np.max(np.abs(out["u_opt_smooth"][:, :, e].T - want["u_opt_smooth"])) <= TOL_COST
+    assert out["status"].shape == (eps.size,)
+
+
+# ------------------------------------------------------------------------------ fused sweep
+def _run_sweep(engine, inp, eps, **kw):
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    return S, wl.run_sweep(engine, batch, eps, **kw)
+
+
+def test_sweep_matches_oracle_and_golden(engine):
+    inp, eps = cases.sweep_case()
+    S, res = _run_sweep(engine, inp, eps, want_front=True, want_u_fore=True, want_u_knee=True, want_P_first=True)
+    g = np.load(os.path.join(GOLD, "sweep.npz"))
+    assert_bits(res["J0"], g["J0"], "J0 golden"); assert_bits(res["J1"], g["J1"], "J1 golden")
+    assert np.array_equal(res["on_front"].astype(bool), g["mask"]) and np.array_equal(res["I_opt"], g["iopt"])
+    nR, nE = g["J0"].shape
+    Tf, L = inp[0]["T"] - inp[0]["T_hist"], 12
+    uf = res["u_fore"].reshape(Tf, L, nR, nE)
+    assert_bits(np.transpose(uf, (2, 3, 1, 0)), g["u_fore"], "u_fore golden")
+    for r in range(nR):
+        assert_bits(res["u_knee"][r].T, g["u_fore"][r, g["iopt"][r]], "knee schedule")
+    assert not res["u_fore"][Tf - 1].any()                   # u_opt_smooth(:,T) == 0 quirk reaches the rollout
+    # live oracle on the same inputs (fixed-input smoother included)
+    o = orc()
+    for r, rin in enumerate(inp):
+        s3 = rin["setup3"]
+        o3 = o.ekf_eks(o.SIALPHA, rin["u_fixed"], rin["x"], s3["params"], s3["s_init"], s3["Ps_init"],
+                       s3["s_final"], s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], rin["R_v"], 1.0,
+                       s3["gamma_ekf"], s3["W"], 1)
+        assert_bits(S[:, :, r].T, o3["S_SMOOTH"], "fixed-input smoother")
+    assert np.max(np.abs(res["J0"] - g["J0"]) / np.abs(g["J0"])) <= TOL_COST
+
+
+def test_sweep_with_noise_waves_and_device_mode(engine):
+    import torch
+    inp, eps = cases.sweep_case(n_regions=2, n_eps=9, T_hist=40, T_fore=20)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    B, Tf = 2 * eps.size, 20
+    rng = np.random.default_rng(77)
+    noise = rng.standard_normal((Tf, 3, B))
+    nstd = np.array([inp[r]["setup3"]["noise_std"] for r in range(2)])
+    ref = wl.run_sweep(engine, batch, eps, noise=noise, noise_std=nstd)
+    o = orc()
+    for r, rin in enumerate(inp):
+        s6 = rin["setup6"]
+        Th = rin["T_hist"]
+        Sr = S[:, :, r].T
+        reg = o.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                            s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21,
+                            Sr[0, Th - 1], Sr[1, Th - 1], Sr[2, Th - 1], (Sr[0, :Th] * Sr[1, :Th]) * Sr[2, :Th],
+                            rin["weights"], noise_std=tuple(nstd[r]),
+                            noise=np.ascontiguousarray(noise[:, :, r * eps.size:(r + 1) * eps.size].transpose(2, 0, 1)))
+        j0, j1, m, io, _ = o.sweep_region(reg, eps)
+        assert_bits(ref["J0"][r], j0, "noisy J0"); assert_bits(ref["J1"][r], j1, "noisy J1")
+        assert np.array_equal(ref["on_front"][r].astype(bool), m) and ref["I_opt"][r] == io
+    engine.set_scratch_limit(5 * 60 * 8 * 200)              # forces several waves
+    try:
+        waved = wl.run_sweep(engine, batch, eps, noise=noise, noise_std=nstd)
+    finally:
+        engine.set_scratch_limit(0)
+    assert_bits(waved["J0"], ref["J0"]); assert_bits(waved["J1"], ref["J1"])
+    dbatch = wl.sweep_to_device(batch, eps, "cuda:0")
+    dres = wl.run_sweep(engine, dbatch, eps, noise=torch.from_numpy(noise).cuda(),
+                        noise_std=torch.from_numpy(nstd).cuda())
+    engine.sync()
+    assert_bits(dres["J0"].cpu().numpy(), ref["J0"]); assert_bits(dres["J1"].cpu().numpy(), ref["J1"])
+    assert np.array_equal(dres["I_opt"].cpu().numpy(), ref["I_opt"])
+
+
+def test_sweep_full_size_properties(engine):
+    """BASELINE config 4 at full size (236 regions x 250 epsilon x (441+120) days): properties
+    that do not need the oracle at scale + an oracle spot check of a few (region, epsilon)."""
+    nR, Th, Tf = 236, 441, 120
+    inp = syn.sweep_inputs(n_regions=nR, T_hist=Th, T_fore=Tf)
+    eps = syn.epsilon_grid_xprize02(250)
+    S, res = _run_sweep(engine, inp, eps, want_front=True, want_u_knee=True)
+    J0, J1, m = res["J0"], res["J1"], res["on_front"].astype(bool)
+    assert J0.shape == (nR, 250) and np.isfinite(J0).all() and np.isfinite(J1).all()
+    assert (J0 >= 0).all() and (J1 >= 0).all()
+    wmax = np.array([np.mean(r["weights"][:, 0] * np.array(r["setup6"]["params"]["u_max"])) for r in inp])
+    assert (J1 <= wmax[:, None] * (1 + 1e-12)).all()          # cost cannot exceed "everything at max"
+    assert m.any(axis=1).all()                                # every region has a non-empty front
+    m2, _ = engine.pareto(np.where(m, J0, np.inf), np.where(m, J1, np.inf))
+    assert np.array_equal(m2.astype(bool) & m, m)             # idempotence
+    umax = np.asarray(inp[0]["setup6"]["params"]["u_max"])
+    uk = res["u_knee"]
+    assert (((uk == 0) | (uk == umax[None, None, :]))).all()  # bang-bang knee schedules
+    o = orc()
+    for r, e in ((0, 0), (17, 124), (123, 125), (235, 249)):
+        rin = inp[r]
+        s6 = rin["setup6"]
+        Sr = S[:, :, r].T
+        reg = o.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                            s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21,
+                            Sr[0, Th - 1], Sr[1, Th - 1], Sr[2, Th - 1], (Sr[0, :Th] * Sr[1, :Th]) * Sr[2, :Th],
+                            rin["weights"])
+        j0, j1, _, _, _ = o.sweep_region(reg, eps[e:e + 1])
+        assert J0[r, e] == j0[0] and J1[r, e] == j1[0], (r, e)
