@@ -18,6 +18,8 @@ Differences forced by the boundary (all documented in DESIGN.md):
     reference; only the four known handle sets can run on the device, named by
     the HANDLES_* constants.  Anything else raises NotImplementedError.
 """
+import atexit
+
 import numpy as np
 
 from . import _capi as K
@@ -31,7 +33,15 @@ def get_engine(device=0):
     global _engine
     if _engine is None:
         _engine = Engine(device)
+        atexit.register(_close_engine)
     return _engine
+
+
+def _close_engine():
+    global _engine
+    if _engine is not None:
+        _engine.close()
+        _engine = None
 
 
 def _K_of(T, dt):

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "epi_device.cuh"
@@ -595,6 +596,12 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
         p.Ps_init_t = w.traj_in(a->Ps_init, MM, B, b0, nb);
         p.s_final_t = w.traj_in(a->s_final, M, B, b0, nb);
         p.Ps_final_t = w.traj_in(a->Ps_final, MM, B, b0, nb);
+      }
+      if (model_flipped(a->model)) {
+        // SIAlphaModelBackwardEKF.m:21-24: the time-reversed filter starts from
+        // (s_final, Ps_final) and its smoother ends on (s_init, Ps_init)
+        std::swap(p.s_init_g, p.s_final_g); std::swap(p.Ps_init_g, p.Ps_final_g);
+        std::swap(p.s_init_t, p.s_final_t); std::swap(p.Ps_init_t, p.Ps_final_t);
       }
       p.v_bar = a->v_bar; p.beta = a->beta; p.gamma = a->gamma;
       p.tape_packed = packed ? 1 : 0;

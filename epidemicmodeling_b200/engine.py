@@ -80,6 +80,11 @@ class Engine:
             self._h = None
 
     def __del__(self):
+        # never call into CUDA while the interpreter (and the CUDA runtime with it) is
+        # being torn down: api.get_engine() registers an atexit close for the shared engine
+        import sys
+        if sys.is_finalizing():
+            return
         try:
             self.close()
         except Exception:
@@ -97,8 +102,11 @@ class Engine:
         self._ck(self._lib.epi_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def use_torch_stream(self):
-        """Run on torch's current stream so torch.cuda.Event timing brackets the kernels."""
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        """Run on torch's current stream so torch.cuda.Event timing brackets the kernels.
+        torch's default stream is the legacy NULL stream; epi_set_stream treats NULL as
+        "the context's own stream", so it is passed as the cudaStreamLegacy handle (0x1)."""
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        self.set_stream(ptr if ptr else 0x1)
 
     def set_scratch_limit(self, nbytes):
         self._ck(self._lib.epi_set_scratch_limit(self._h, int(nbytes)))

@@ -88,7 +88,9 @@ typedef struct epi_ctx epi_ctx;
 int epi_create(int device, epi_ctx **ctx);
 void epi_destroy(epi_ctx *ctx);
 const char *epi_last_error(const epi_ctx *ctx); /* ctx may be NULL: last create error */
-int epi_set_stream(epi_ctx *ctx, void *cuda_stream); /* cudaStream_t; NULL = own stream */
+/* cudaStream_t to enqueue on; NULL = the context's own (non-blocking) stream.  To use the
+ * legacy default stream pass the cudaStreamLegacy handle ((void *)0x1). */
+int epi_set_stream(epi_ctx *ctx, void *cuda_stream);
 int epi_sync(epi_ctx *ctx);
 /* cap on library-owned scratch (tape) bytes; larger batches are processed in
  * waves of trajectories.  0 = default (60 % of free device memory). */
