@@ -17,8 +17,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libepi_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
-SOURCES = ["capi.cu", "ekf_kernels.cu", "other_kernels.cu"]
-HEADERS = [os.path.join(CSRC, h) for h in ("epi_device.cuh", "epi_internal.h", "epi_linalg.cuh")] + \
+SOURCES = ["capi.cu", "ekf_forward.cu", "eks_gain.cu", "eks_backward.cu", "other_kernels.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("epi_device.cuh", "epi_internal.h", "epi_linalg.cuh", "ekf_common.cuh")] + \
           [os.path.join(ROOT, "include", "epi_b200.h")]
 NVCC_FLAGS = ["-O3", "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -39,18 +39,19 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile (if sources changed) and return the path of libepi_b200.so."""
-    stamp = os.path.join(OBJ_DIR, "stamp")
-    dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
-        return LIB
-    os.makedirs(OBJ_DIR, exist_ok=True)
+def build(force=False, verbose=False, extra_flags=(), lib=LIB, obj_dir=OBJ_DIR):
+    """Compile (if sources changed) and return the path of libepi_b200.so.
+    extra_flags/lib/obj_dir build kernel-variant experiments (e.g. -DEPI_GAIN_MIN_BLOCKS=4)."""
+    stamp = os.path.join(obj_dir, "stamp")
+    dig = _digest() + " ".join(extra_flags)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return lib
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         with open(obj + ".log", "w") as fh:
             fh.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
@@ -62,13 +63,13 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(stamp, "w") as fh:
         fh.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libepi_b200.so")
+LIB_PATH = os.environ.get("EPI_B200_LIB") or os.path.join(PKG, "libepi_b200.so")  # env: kernel-variant experiments
 
 LMAX = 12
 MEM_HOST, MEM_DEVICE = 0, 1

@@ -149,9 +149,14 @@ struct Call {
                     (size_t)Bw * sizeof(double), rows});
     return TArr{d, Bw, 0};
   }
-  // library scratch [rows][Bw]
+  // library scratch [rows][Bw] in the caller-style strided layout
   TArr scratch(size_t rows, long long Bw) {
     return TArr{(double *)dalloc(rows * (size_t)Bw * sizeof(double)), Bw, 0};
+  }
+  // library scratch in the tile layout [ceil(Bw/32)][rows][32] (ekf_common.cuh)
+  TArr scratch_tiled(size_t rows, long long Bw) {
+    const size_t tiles = (size_t)((Bw + 31) / 32);
+    return TArr{(double *)dalloc(tiles * rows * 32 * sizeof(double)), 32, 0};
   }
   void flush() {
     for (auto &k : pend)
@@ -557,8 +562,18 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
 
     // scratch / staging bytes per trajectory
     const bool host = a->mem == EPI_MEM_HOST;
-    const bool packed = !legacy && !a->P_MINUS && !a->P_PLUS;
-    const int PF = packed ? M * (M + 1) / 2 : MM;
+    // tile layout (+ packed symmetric P pages) when the whole tape is library scratch
+    const bool tiled = !a->S_MINUS && !a->S_PLUS && !a->P_MINUS && !a->P_PLUS;
+    const int PF = (tiled && !legacy) ? M * (M + 1) / 2 : MM;
+    // per-(group, day) input pre-pass (only meaningful when u is shared by the group)
+    double *dot_grp = nullptr;
+    if (!a->u_per_traj) {
+      dot_grp = (double *)shared.dalloc((size_t)n_groups * T * 8);
+      PhaseScope ph(c, "group_day");
+      launch_group_day(prm, u_grp, nullptr, (int)n_groups, T, L, dot_grp, nullptr, c->stream);
+      check_launch(c, 1);
+      ph.end();
+    }
     size_t per = (size_t)(T - 1) * MM * 8;  // J
     if (!a->S_MINUS || host) per += (size_t)T * M * 8;
     if (!a->S_PLUS || host) per += (size_t)T * M * 8;
@@ -604,12 +619,20 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
         std::swap(p.s_init_t, p.s_final_t); std::swap(p.Ps_init_t, p.Ps_final_t);
       }
       p.v_bar = a->v_bar; p.beta = a->beta; p.gamma = a->gamma;
-      p.tape_packed = packed ? 1 : 0;
-      p.S_MINUS = a->S_MINUS ? w.traj_out(a->S_MINUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
-      p.S_PLUS = a->S_PLUS ? w.traj_out(a->S_PLUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
-      p.P_MINUS = a->P_MINUS ? w.traj_out(a->P_MINUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * PF, nb);
-      p.P_PLUS = a->P_PLUS ? w.traj_out(a->P_PLUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * PF, nb);
-      p.J = w.scratch((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
+      p.tiled = tiled ? 1 : 0;
+      p.dot_grp = dot_grp; p.cost_grp = nullptr;
+      if (tiled) {
+        p.S_MINUS = w.scratch_tiled((size_t)T * M, nb);
+        p.S_PLUS = w.scratch_tiled((size_t)T * M, nb);
+        p.P_MINUS = w.scratch_tiled((size_t)T * PF, nb);
+        p.P_PLUS = w.scratch_tiled((size_t)T * PF, nb);
+      } else {
+        p.S_MINUS = a->S_MINUS ? w.traj_out(a->S_MINUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
+        p.S_PLUS = a->S_PLUS ? w.traj_out(a->S_PLUS, (size_t)T * M, B, b0, nb) : w.scratch((size_t)T * M, nb);
+        p.P_MINUS = a->P_MINUS ? w.traj_out(a->P_MINUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * MM, nb);
+        p.P_PLUS = a->P_PLUS ? w.traj_out(a->P_PLUS, (size_t)T * MM, B, b0, nb) : w.scratch((size_t)T * MM, nb);
+      }
+      p.J = w.scratch_tiled((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
       p.u_opt = w.traj_out(a->u_opt, (size_t)T * L, B, b0, nb);
       p.u_opt_smooth = legacy ? TArr{nullptr, 0, 0} : w.traj_out(a->u_opt_smooth, (size_t)T * L, B, b0, nb);
       p.S_SMOOTH = w.traj_out(a->S_SMOOTH, (size_t)T * M, B, b0, nb);
@@ -730,6 +753,15 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     if (a->u_fore && host)
       shared.pend.push_back({a->u_fore, u_fore_dev, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, 1});
 
+    // per-(region, day) input pre-pass: days whose NPIs are all given share their input term and cost
+    double *dot_grp = (double *)shared.dalloc((size_t)nR * T * 8);
+    double *cost_grp = (double *)shared.dalloc((size_t)nR * T * 8);
+    {
+      PhaseScope ph(c, "group_day");
+      launch_group_day(prm, u, wts, (int)nR, T, L, dot_grp, cost_grp, c->stream);
+      check_launch(c, 1);
+      ph.end();
+    }
     size_t per = (size_t)(T - 1) * MM * 8 + (size_t)2 * T * M * 8 + (size_t)2 * T * PF * 8 + (size_t)2 * T * 8;
     if (host && a->noise) per += (size_t)Tf * 24;
     if (host && a->P_first) per += (size_t)MM * 8;
@@ -748,14 +780,15 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       p.init_per_traj = 0;
       p.s_init_g = s_init; p.Ps_init_g = Ps_init; p.s_final_g = s_final; p.Ps_final_g = Ps_final;
       p.v_bar = 0.0; p.beta = a->beta_ekf; p.gamma = a->gamma_ekf;
-      p.tape_packed = 1;
-      p.S_MINUS = w.scratch((size_t)T * M, nb);
-      p.S_PLUS = w.scratch((size_t)T * M, nb);
-      p.P_MINUS = w.scratch((size_t)T * PF, nb);
-      p.P_PLUS = w.scratch((size_t)T * PF, nb);
-      p.J = w.scratch((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
-      p.dot_day = w.scratch(T, nb);
-      p.cost_day = w.scratch(T, nb);
+      p.tiled = 1;
+      p.dot_grp = dot_grp; p.cost_grp = cost_grp;
+      p.S_MINUS = w.scratch_tiled((size_t)T * M, nb);
+      p.S_PLUS = w.scratch_tiled((size_t)T * M, nb);
+      p.P_MINUS = w.scratch_tiled((size_t)T * PF, nb);
+      p.P_PLUS = w.scratch_tiled((size_t)T * PF, nb);
+      p.J = w.scratch_tiled((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
+      p.dot_day = w.scratch_tiled(T, nb);
+      p.cost_day = w.scratch_tiled(T, nb);
       p.weights = wts;
       p.T_hist = a->T_hist;
       if (u_fore_dev) p.u_fore = TArr{u_fore_dev, B, b0};
@@ -785,8 +818,8 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       r.noise = w.traj_in(a->noise, (size_t)Tf * 3, B, b0, nb);
       r.T_total = T; r.T_hist = a->T_hist;
       r.newcases_hist = nch;
-      r.dot_day = CArr{p.dot_day.p, p.dot_day.stride, p.dot_day.off};
-      r.cost_day = CArr{p.cost_day.p, p.cost_day.stride, p.cost_day.off};
+      r.dot_day = p.dot_day.p;
+      r.cost_day = p.cost_day.p;
       r.J0 = TArr{J0, B, b0};
       r.J1 = TArr{J1, B, b0};
       {

@@ -1,0 +1,312 @@
+// ekf_forward.cu -- EKF forward pass for batches of independent trajectories
+// (sm_100a, FP64, --fmad=false) + the per-group/per-day input pre-pass.
+//
+// Reference behaviour: Tools/GenericExtendedKalmanFilter.m:98-186 (generic models) and
+// Tools/NewCaseEKFEstimatorWithOptimalNPI.m:40-114 (legacy models).
+//
+// One thread per trajectory, strictly sequential in time.  State, covariance (packed
+// symmetric for the generic models), gain and Jacobian stay in registers; loop-invariant
+// model scalars are read once; the per-day tape (S_MINUS, S_PLUS, P_MINUS, P_PLUS) is
+// written so that every store instruction of a warp is one contiguous 256-byte row
+// (tiled scratch: all offsets are instruction immediates).
+#include "ekf_common.cuh"
+
+namespace epi {
+
+// ===========================================================================
+// per-(group, day) input pre-pass
+// ===========================================================================
+// On a day whose NPI inputs are all given (no NaN to optimise), the input term
+// gamma*a'*(u_max - u) (SIAlphaModelEKF.m:46 / ...OptControlled.m:67), A(3,6) = 0 and the
+// day's weighted cost sum_j w*u do not depend on the trajectory: evaluate them once per
+// (group, day) with the SAME operation sequence the per-trajectory code uses.  A NaN result
+// means "evaluate per trajectory" (a NaN input, or NaN parameters -- the per-trajectory
+// path then reproduces the same NaN), so the shortcut can never change a result.
+__global__ void __launch_bounds__(128) group_day_kernel(const epi_model_params *__restrict__ prm,
+                                                        const double *__restrict__ u,
+                                                        const double *__restrict__ weights, int n_groups,
+                                                        int T, int L, double *__restrict__ dot_grp,
+                                                        double *__restrict__ cost_grp) {
+  const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (size_t)n_groups * T) return;
+  const int g = (int)(q / T);
+  const epi_model_params *__restrict__ p = prm + g;
+  const double *__restrict__ ud = u + q * L;
+  const double gamma = p->gamma;
+  double dot = 0.0, cost = 0.0;
+  bool has_nan = false;
+  for (int j = 0; j < L; ++j) {
+    const double uj = ud[j];
+    has_nan |= (uj != uj);
+    const double gj = gamma * p->a[j];
+    const double d = p->u_max[j] - uj;
+    dot = (j == 0) ? gj * d : fma(gj, d, dot);
+    if (weights) {
+      const double wu = weights[q * L + j] * uj;
+      cost = (j == 0) ? wu : (cost + wu);
+    }
+  }
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  dot_grp[q] = has_nan ? nan : dot;
+  if (cost_grp) cost_grp[q] = has_nan ? nan : cost;
+}
+void launch_group_day(const epi_model_params *prm, const double *u, const double *weights, int n_groups,
+                      int T, int L, double *dot_grp, double *cost_grp, cudaStream_t st) {
+  const size_t total = (size_t)n_groups * T;
+  if (!total) return;
+  group_day_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(prm, u, weights, n_groups, T, L, dot_grp,
+                                                                     cost_grp);
+}
+
+// ===========================================================================
+// forward pass
+// ===========================================================================
+template <int MODEL, bool MONITOR, bool TILED>
+__global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__ EkfParams P) {
+  constexpr int M = model_dim(MODEL);
+  constexpr bool LEG = model_legacy(MODEL);
+  constexpr bool SYM = !LEG;
+  constexpr bool REV = model_flipped(MODEL);
+  constexpr int MM = M * M;
+  constexpr int PF = (SYM && TILED) ? M * (M + 1) / 2 : MM;
+  extern __shared__ double win[];  // MONITOR: [3][W][blockDim.x]
+
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const TrajIn in = traj_inputs(P, b, M);
+  const ModelConsts mc = load_consts(in.prm);
+  const int T = P.T, L = P.L, W = P.W;
+  const double gamma = P.gamma, beta = P.beta, v_bar = P.v_bar, eps = in.eps;
+
+  const Tape<TILED> tSm = make_tape<TILED>(P.S_MINUS, M, T, b), tSp = make_tape<TILED>(P.S_PLUS, M, T, b);
+  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T, b), tPp = make_tape<TILED>(P.P_PLUS, PF, T, b);
+
+  double s[M];
+  Mat<M, SYM> Pm;  // P(k|k-1)
+  if (P.init_per_traj) {
+    const double *si = P.s_init_t.p + P.s_init_t.off + b;
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = si[(size_t)i * P.s_init_t.stride];
+    load_mat<M, SYM>(Pm, P.Ps_init_t.p + P.Ps_init_t.off + b, (size_t)P.Ps_init_t.stride);
+  } else {
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = P.s_init_g[in.g * M + i];
+    load_mat<M, SYM>(Pm, P.Ps_init_g + (size_t)in.g * MM, 1);
+  }
+
+  if (MONITOR) {
+    for (int j = 0; j < 3 * W; ++j) win[(size_t)j * blockDim.x + threadIdx.x] = 0.0;
+  }
+  int head = 0;               // ring position of the newest window slot
+  double R_over = 0.0;        // adapted R for the next step (:184)
+  bool has_over = false;
+
+  for (int k = 0; k < T; ++k) {
+    const int pos = REV ? (T - 1 - k) : k;
+    // :100-101 store the a-priori estimate
+    {
+      double *__restrict__ d = tSm.at_day(pos);
+#pragma unroll
+      for (int i = 0; i < M; ++i) d[tSm.f(i)] = s[i];
+      tape_store_cov<M, SYM, TILED>(Pm, tPm, tPm.at_day(pos));
+    }
+
+    double Rk;
+    if (LEG) {
+      Rk = (k == 0) ? in.R_const : R_over;  // scalar R adapted in place (:31,:111)
+    } else {
+      const double base = (P.r_mode == EPI_R_CONST) ? in.R_const : __ldg(in.R + (size_t)k * in.R_ts);
+      Rk = has_over ? R_over : base;
+      has_over = false;
+    }
+    double C[3];
+    const double xhat = obs_model<MODEL>(mc.obs_type, s, v_bar, C);  // :115-119
+    const double xk = __ldg(in.x + (size_t)pos * in.x_ts);
+    const bool valid = !(xk != xk);                               // :122
+
+    double K[M], sp[M], innov;
+    Mat<M, SYM> Pp;  // P(k|k)
+    if (valid) {
+      innov = xk - xhat;  // :123
+      double PCt[M], CP[3];
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        PCt[i] = fma(Pm(i, 2), C[2], fma(Pm(i, 1), C[1], Pm(i, 0) * C[0]));
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        CP[j] = fma(C[2], Pm(2, j), fma(C[1], Pm(1, j), C[0] * Pm(0, j)));
+      const double S0 = fma(CP[2], C[2], fma(CP[1], C[1], CP[0] * C[0]));
+      const double denom = S0 + gamma * Rk;  // :124 (+ Gsp + Gvp = 0)
+#pragma unroll
+      for (int i = 0; i < M; ++i) K[i] = PCt[i] / denom;
+      double Mx[M][3];  // I - K*C, columns 0..2 (columns 3.. are identity)
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Mx[i][j] = ((i == j) ? 1.0 : 0.0) - K[i] * C[j];
+      Mat<M, false> MP;
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          double acc = fma(Mx[i][2], Pm(2, j), fma(Mx[i][1], Pm(1, j), Mx[i][0] * Pm(0, j)));
+          if (i >= 3) acc = acc + Pm(i, j);
+          MP.at(i, j) = acc;
+        }
+      if (LEG) {
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = 0; j < M; ++j) Pp.at(i, j) = MP(i, j) / gamma;  // legacy :64
+      } else {
+        // :127 Joseph form, :138 symmetrisation
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = i; j < M; ++j) {
+            double mij = fma(MP(i, 2), Mx[j][2], fma(MP(i, 1), Mx[j][1], MP(i, 0) * Mx[j][0]));
+            if (j >= 3) mij = mij + MP(i, j);
+            double mji = fma(MP(j, 2), Mx[i][2], fma(MP(j, 1), Mx[i][1], MP(j, 0) * Mx[i][0]));
+            if (i >= 3) mji = mji + MP(j, i);
+            const double pij = (mij + (K[i] * Rk) * K[j]) / gamma;
+            const double pji = (mji + (K[j] * Rk) * K[i]) / gamma;
+            Pp.at(i, j) = (pij + pji) / 2.0;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < M; ++i) sp[i] = s[i] + K[i] * innov;  // :129
+    } else {  // :131-134
+      innov = 0.0;
+#pragma unroll
+      for (int i = 0; i < M; ++i) { K[i] = 0.0; sp[i] = s[i]; }
+      if (LEG) {
+        Pp = Pm;
+      } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = i; j < M; ++j) Pp.at(i, j) = (Pm(i, j) + Pm(j, i)) / 2.0;  // :138
+      }
+    }
+    state_margins<MODEL>(mc, sp);  // :141
+
+    // :155-157 state update + Jacobian at s(k|k) (one pass over the NPI inputs, or the
+    // per-group value when the day has no input to optimise)
+    double *uo = P.u_opt.p ? P.u_opt.p + (size_t)P.u_opt.off + b + (size_t)pos * L * P.u_opt.stride : nullptr;
+    const double *ud = in.u + (size_t)pos * in.u_ts;
+    double dotv, a25 = 0.0;
+    const double pre = in.dot_grp ? __ldg(in.dot_grp + pos) : __longlong_as_double(0x7ff8000000000000ll);
+    if (pre == pre) {
+      dotv = pre;
+      if (uo) {
+#pragma unroll
+        for (int j = 0; j < EPI_LMAX; ++j)
+          if (j < L) uo[(size_t)j * P.u_opt.stride] = ud[(size_t)j * in.u_js];
+      }
+    } else {
+      const InputPass ip = input_pass<MODEL, true, false>(mc, eps, (M == 6) ? sp[M - 1] : 0.0, ud, in.u_js, L, uo,
+                                                          (size_t)P.u_opt.stride, nullptr);
+      dotv = ip.dot;
+      a25 = ip.a25;
+    }
+    double sn[M];
+    state_eqs<MODEL>(mc, eps, sp, dotv, sn);
+    Mat<M, false> A;
+    state_jacobian<MODEL>(mc, eps, sp, a25, A);
+    Mat<M, false> AP;
+    mul_A_P<M, SYM>(A, Pp, AP);
+    // :158 P(k+1|k) = A P A' + Q, :161 symmetrisation
+    if (LEG) {
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = 0; j < M; ++j)
+          Pm.at(i, j) = mul_X_At_ij<M, false>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
+    } else {
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int j = i; j < M; ++j) {
+          const double pij = mul_X_At_ij<M, false>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
+          const double pji = mul_X_At_ij<M, false>(AP, A, j, i) + q_elem(in.Q, P.q_mode, M, k, j, i);
+          Pm.at(i, j) = (pij + pji) / 2.0;
+        }
+    }
+    state_margins<MODEL>(mc, sn);  // :164
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = sn[i];
+
+    // :167-169
+    {
+      double *__restrict__ d = tSp.at_day(pos);
+#pragma unroll
+      for (int i = 0; i < M; ++i) d[tSp.f(i)] = sp[i];
+      tape_store_cov<M, SYM, TILED>(Pp, tPp, tPp.at_day(pos));
+    }
+    if (P.K_GAIN.p) {
+      double *d = P.K_GAIN.p + (size_t)P.K_GAIN.off + b + (size_t)pos * M * P.K_GAIN.stride;
+#pragma unroll
+      for (int i = 0; i < M; ++i) d[(size_t)i * P.K_GAIN.stride] = K[i];
+    }
+    if (P.innov.p) P.innov.p[(size_t)pos * P.innov.stride + P.innov.off + b] = innov;
+
+    if (MONITOR) {
+      // :172-185 innovation whiteness monitor.  The three W-long windows live in
+      // shared memory as ring buffers; sums run newest -> oldest over all W
+      // slots (leading zeros included), as the reference's cat() windows do.
+      const int cnt = (k + 1 < W) ? (k + 1) : W;
+      head = (head == 0) ? (W - 1) : (head - 1);
+      double *wm = win + threadIdx.x;
+      const size_t bs = blockDim.x;
+      wm[(size_t)(0 * W + head) * bs] = innov;
+      double sm = 0.0;
+      for (int j = 0, q = head; j < W; ++j) { sm += wm[(size_t)(0 * W + q) * bs]; q = (q + 1 == W) ? 0 : q + 1; }
+      const double mu = sm / (double)cnt;
+      const double cc = (innov - mu) * (innov - mu);
+      wm[(size_t)(1 * W + head) * bs] = cc;
+      wm[(size_t)(2 * W + head) * bs] = LEG ? (cc / Rk) : (cc / (Rk + kEps));  // :178 / legacy :108
+      double sn_ = 0.0;
+      for (int j = 0, q = head; j < W; ++j) { sn_ += wm[(size_t)(2 * W + q) * bs]; q = (q + 1 == W) ? 0 : q + 1; }
+      if (P.rho.p) P.rho.p[(size_t)k * P.rho.stride + P.rho.off + b] = sn_ / (double)cnt;  // rho is NOT time-flipped
+      const bool adapt = LEG ? (beta != 1.0 && valid)
+                             : (beta != 1.0 && valid && P.fixed_R && (k + 1 < T));  // :180 / :110
+      if (adapt) {
+        double sc = 0.0;
+        for (int j = 0, q = head; j < W; ++j) { sc += wm[(size_t)(1 * W + q) * bs]; q = (q + 1 == W) ? 0 : q + 1; }
+        if (LEG) R_over = beta * Rk + ((1.0 - beta) * sc) / (double)cnt;   // legacy :111
+        else     R_over = beta * Rk + (1.0 - beta) * (sc / (double)cnt);   // :182-184
+        has_over = true;
+      } else if (LEG) {
+        R_over = Rk;
+      }
+    } else if (LEG) {
+      R_over = Rk;
+    }
+  }
+}
+
+template <int MODEL, bool TILED>
+static void launch_fwd_model(const EkfParams &p, cudaStream_t st, bool monitor) {
+  const int block = (model_dim(MODEL) == 6) ? 32 : 64;
+  const int grid = (p.B + block - 1) / block;
+  if (monitor) {
+    const size_t smem = (size_t)3 * p.W * block * sizeof(double);
+    cudaFuncSetAttribute(ekf_forward_kernel<MODEL, true, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    ekf_forward_kernel<MODEL, true, TILED><<<grid, block, smem, st>>>(p);
+  } else {
+    ekf_forward_kernel<MODEL, false, TILED><<<grid, block, 0, st>>>(p);
+  }
+}
+
+void launch_ekf_forward(const EkfParams &p, cudaStream_t st) {
+  // the monitor is dead code unless rho is wanted or R adapts (beta != 1)
+  const bool monitor = (p.rho.p != nullptr) || (p.beta != 1.0);
+#define CALL(MDL)                                                  \
+  if (p.tiled) launch_fwd_model<MDL, true>(p, st, monitor);        \
+  else launch_fwd_model<MDL, false>(p, st, monitor)
+  EPI_DISPATCH_MODEL(p.model, CALL)
+#undef CALL
+}
+
+}  // namespace epi

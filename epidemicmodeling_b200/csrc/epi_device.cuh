@@ -87,16 +87,33 @@ EPI_DI void store_mat(const Mat<M, SYM> &P, double *__restrict__ base, size_t B)
 // model callbacks
 // ---------------------------------------------------------------------------
 
+// Loop-invariant scalars of the reference's `params` struct, read once per thread
+// (the compiler cannot hoist them itself: tape stores may alias the struct).
+struct ModelConsts {
+  double dt, beta, gamma, b, alpha_min, alpha_max, s_min, i_min, sigma;
+  int obs_type;
+  const epi_model_params *p;  // per-NPI tables a, u_min, u_max, w (read-only path)
+};
+EPI_DI ModelConsts load_consts(const epi_model_params *__restrict__ p) {
+  ModelConsts c;
+  c.dt = __ldg(&p->dt); c.beta = __ldg(&p->beta); c.gamma = __ldg(&p->gamma); c.b = __ldg(&p->b);
+  c.alpha_min = __ldg(&p->alpha_min); c.alpha_max = __ldg(&p->alpha_max);
+  c.s_min = __ldg(&p->s_min); c.i_min = __ldg(&p->i_min); c.sigma = __ldg(&p->sigma);
+  c.obs_type = __ldg(&p->obs_type);
+  c.p = p;
+  return c;
+}
+
 // StateHardMargins: SIAlphaModelEKF.m:27-31 (s_min/i_min floors); every other
 // model clamps s,i to [0,1] (SIAlphaModelBackwardEKF.m:48-52,
 // SIAlphaModelEKFOptControlled.m:27-31, NewCaseEKFEstimatorWithOptimalNPI.m:150-154).
 template <int MODEL>
-EPI_DI void state_margins(const epi_model_params *__restrict__ p, double *s) {
-  const double lo_s = (MODEL == EPI_MODEL_SIALPHA) ? p->s_min : 0.0;
-  const double lo_i = (MODEL == EPI_MODEL_SIALPHA) ? p->i_min : 0.0;
+EPI_DI void state_margins(const ModelConsts &c, double *s) {
+  const double lo_s = (MODEL == EPI_MODEL_SIALPHA) ? c.s_min : 0.0;
+  const double lo_i = (MODEL == EPI_MODEL_SIALPHA) ? c.i_min : 0.0;
   s[0] = mmin(1.0, mmax(lo_s, s[0]));
   s[1] = mmin(1.0, mmax(lo_i, s[1]));
-  s[2] = mmin(p->alpha_max, mmax(p->alpha_min, s[2]));
+  s[2] = mmin(c.alpha_max, mmax(c.alpha_min, s[2]));
 }
 
 // One pass over the L NPI inputs of a day.  Fuses what the reference does in
@@ -110,28 +127,29 @@ struct InputPass {
   double cost;  // sum_j w_day[j] * u_opt[j]   (NPICost's weights.*inputs for this day)
 };
 template <int MODEL, bool WANT_A25, bool WANT_COST>
-EPI_DI InputPass input_pass(const epi_model_params *__restrict__ p, double eps, double s5,
+EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
                             const double *__restrict__ u, size_t u_stride, int L,
                             double *__restrict__ u_out, size_t uo_stride,
                             const double *__restrict__ w_day) {
   constexpr bool SIX = model_dim(MODEL) == 6;
   constexpr bool FLIP = model_flipped(MODEL);
+  const epi_model_params *__restrict__ p = c.p;
   InputPass r;
   r.dot = 0.0; r.a25 = 0.0; r.cost = 0.0;
-  const double gamma = p->gamma;
+  const double gamma = c.gamma;
   const double gs = SIX ? gamma * s5 : 0.0;
-  const double lo = SIX ? (-1.0) / p->sigma : 0.0, hi = SIX ? 1.0 / p->sigma : 0.0;
-  const double slope = (SIX && WANT_A25) ? (gamma * p->dt) * (p->sigma / 2.0) : 0.0;
+  const double lo = SIX ? (-1.0) / c.sigma : 0.0, hi = SIX ? 1.0 / c.sigma : 0.0;
+  const double slope = (SIX && WANT_A25) ? (gamma * c.dt) * (c.sigma / 2.0) : 0.0;
 #pragma unroll
   for (int j = 0; j < EPI_LMAX; ++j) {
     if (j < L) {
       double uj = u[(size_t)j * u_stride];
-      const double aj = p->a[j];
-      const double umax = p->u_max[j];
+      const double aj = __ldg(&p->a[j]);
+      const double umax = __ldg(&p->u_max[j]);
       if (SIX) {
-        const double phi = eps * p->w[j] - gs * aj;
         if (uj != uj) {
-          const double umin = p->u_min[j];
+          const double phi = eps * __ldg(&p->w[j]) - gs * aj;
+          const double umin = __ldg(&p->u_min[j]);
           if (WANT_A25) {
             if (phi > lo && phi < hi) {
               const double term = (slope * aj) * (umax - umin);
@@ -159,12 +177,11 @@ EPI_DI InputPass input_pass(const epi_model_params *__restrict__ p, double eps, 
 // (SIAlphaModelEKF.m:44-46, SIAlphaModelBackwardEKF.m:65-67,
 //  SIAlphaModelEKFOptControlled.m:60-72, ...BackwardEKFOptControlled.m:81-93)
 template <int MODEL>
-EPI_DI void state_eqs(const epi_model_params *__restrict__ p, double eps, const double *s,
-                      double dot, double *sn) {
+EPI_DI void state_eqs(const ModelConsts &c, double eps, const double *s, double dot, double *sn) {
   constexpr bool SIX = model_dim(MODEL) == 6;
   constexpr bool FLIP = model_flipped(MODEL);
-  const double dt = p->dt, beta = p->beta, gamma = p->gamma;
-  const double f2 = (((-gamma) * s[2]) + gamma * p->b) + dot;
+  const double dt = c.dt, beta = c.beta, gamma = c.gamma;
+  const double f2 = (((-gamma) * s[2]) + gamma * c.b) + dot;
   double x0, x1, x2;
   if (!FLIP) {
     x0 = s[0] - ((dt * s[2]) * s[0]) * s[1];
@@ -175,11 +192,11 @@ EPI_DI void state_eqs(const epi_model_params *__restrict__ p, double eps, const 
     x1 = s[1] - dt * (((s[2] * s[0]) * s[1]) - beta * s[1]);
     x2 = s[2] - dt * f2;
   }
-  const double lo_s = (MODEL == EPI_MODEL_SIALPHA) ? p->s_min : 0.0;
-  const double lo_i = (MODEL == EPI_MODEL_SIALPHA) ? p->i_min : 0.0;
+  const double lo_s = (MODEL == EPI_MODEL_SIALPHA) ? c.s_min : 0.0;
+  const double lo_i = (MODEL == EPI_MODEL_SIALPHA) ? c.i_min : 0.0;
   sn[0] = mmax(lo_s, mmin(1.0, x0));
   sn[1] = mmax(lo_i, mmin(1.0, x1));
-  sn[2] = mmax(p->alpha_min, mmin(p->alpha_max, x2));
+  sn[2] = mmax(c.alpha_min, mmin(c.alpha_max, x2));
   if (SIX) {
     const double rho = (s[3] - s[4]) - (1.0 - eps);
     if (!FLIP) {
@@ -199,11 +216,11 @@ EPI_DI void state_eqs(const epi_model_params *__restrict__ p, double eps, const 
 // NewCaseEKFEstimatorWithOptimalNPI.m:211-257).  Only the structural non-zeros
 // (a_nz) are written; B = I is structural.
 template <int MODEL>
-EPI_DI void state_jacobian(const epi_model_params *__restrict__ p, double eps, const double *s,
-                           double a25, Mat<model_dim(MODEL), false> &A) {
+EPI_DI void state_jacobian(const ModelConsts &c, double eps, const double *s, double a25,
+                           Mat<model_dim(MODEL), false> &A) {
   constexpr bool SIX = model_dim(MODEL) == 6;
   constexpr bool FLIP = model_flipped(MODEL);
-  const double dt = p->dt, beta = p->beta, gamma = p->gamma;
+  const double dt = c.dt, beta = c.beta, gamma = c.gamma;
   if (!FLIP) {
     A.at(0, 0) = 1.0 - (dt * s[2]) * s[1];
     A.at(0, 1) = ((-dt) * s[2]) * s[0];

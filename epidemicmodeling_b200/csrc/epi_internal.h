@@ -45,21 +45,26 @@ struct EkfParams {
   double v_bar, beta, gamma;
   // the forward tape (always present: caller outputs or scratch)
   TArr S_MINUS, S_PLUS, P_MINUS, P_PLUS;
-  int tape_packed;                 // 1: P_MINUS/P_PLUS scratch holds the packed upper triangle
-                                   //    ([T][m(m+1)/2][B], generic models only)
-  TArr J;                          // scratch smoother gains [T-1][m*m][B]
+  int tiled;                       // 1: all four tape arrays are library scratch in the tile layout
+                                   //    [b/32][T][F][32] (ekf_common.cuh); P pages of the generic
+                                   //    models then hold the packed upper triangle (F = m(m+1)/2)
+  TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1][m*m][32]
+  const double *dot_grp;           // per group [T]: input term of days without NaN inputs (NaN = per trajectory)
+  const double *cost_grp;          // per group [T]: that day's sum_j w*u (sweep), or null
   // optional outputs
   TArr u_opt, u_opt_smooth, S_SMOOTH, P_SMOOTH, K_GAIN, innov, rho;
   int *status;                     // [B] of this wave, or null
   // sweep extras: per-day scalars consumed by the fused rollout
-  TArr dot_day;                    // [T][B] gamma*a'*(u_max - u_opt_smooth(:,t))
-  TArr cost_day;                   // [T][B] sum_j w(j,t)*u_opt_smooth(j,t)
+  TArr dot_day;                    // tiled [b/32][T][1][32]: gamma*a'*(u_max - u_opt_smooth(:,t))
+  TArr cost_day;                   // tiled [b/32][T][1][32]: sum_j w(j,t)*u_opt_smooth(j,t)
   const double *weights;           // per group [T][L]
   TArr u_fore;                     // [T-T_hist][L][B]
   int T_hist;
   TArr P_first;                    // [m*m][B]
 };
 
+void launch_group_day(const epi_model_params *prm, const double *u, const double *weights, int n_groups,
+                      int T, int L, double *dot_grp, double *cost_grp, cudaStream_t st);
 void launch_ekf_forward(const EkfParams &p, cudaStream_t st);
 void launch_eks_gain(const EkfParams &p, cudaStream_t st);
 void launch_eks_backward(const EkfParams &p, cudaStream_t st);
@@ -86,7 +91,7 @@ struct RolloutParams {
   int T_total, T_hist;
   const double *j0_prefix, *j1_prefix, *w;    // per group
   const double *newcases_hist;    // sweep: per group [T_hist] (summed in-kernel)
-  CArr dot_day, cost_day;         // sweep: [T][B]
+  const double *dot_day, *cost_day;  // sweep: tiled [b/32][T_total][1][32] of this wave
   TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);

@@ -101,9 +101,11 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   double sd_s = 0.0, sd_i = 0.0, sd_a = 0.0;
   if (P.noise_std) { sd_s = P.noise_std[3 * g + 0]; sd_i = P.noise_std[3 * g + 1]; sd_a = P.noise_std[3 * g + 2]; }
   const bool want_cost = P.J0.p != nullptr;
-  const size_t ds = (size_t)P.dot_day.stride, cs = (size_t)P.cost_day.stride;
-  const double *__restrict__ dotp = (U_KIND == 2) ? P.dot_day.p + P.dot_day.off + b : nullptr;
-  const double *__restrict__ costp = (U_KIND == 2 && P.cost_day.p) ? P.cost_day.p + P.cost_day.off + b : nullptr;
+  // sweep: per-day scalars in the tile layout [b/32][T_total][1][32] written by eks_backward
+  const size_t ds = 32, cs = 32;
+  const size_t tile_off = ((size_t)(b >> 5) * (size_t)P.T_total) * 32 + (size_t)(b & 31);
+  const double *__restrict__ dotp = (U_KIND == 2) ? P.dot_day + tile_off : nullptr;
+  const double *__restrict__ costp = (U_KIND == 2 && P.cost_day) ? P.cost_day + tile_off : nullptr;
   // NPICost accumulators continue over the history
   double a0 = 0.0, a1 = 0.0;
   if (want_cost) {

@@ -1,0 +1,120 @@
+"""Summarise ncu captures brought back in gpurun_out/ into profiles/ (tracked).
+
+    python tools/ncu_summary.py r01            # round tag
+
+Reads  gpurun_out/launches.csv   (ncu --metrics gpu__time_duration.sum launch list)
+       gpurun_out/prof_*.ncu-rep  (ncu --set full, one kernel each)
+Writes profiles/<tag>_launches.csv (copy), profiles/<tag>_launch_shares.md and
+       profiles/<tag>_<kernel>.md (key raw metrics + top stall reasons per source line).
+"""
+import csv
+import glob
+import io
+import os
+import re
+import shutil
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GO = os.path.join(ROOT, "gpurun_out")
+PR = os.path.join(ROOT, "profiles")
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+    "launch__waves_per_multiprocessor", "launch__grid_size", "launch__block_size",
+    "sm__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "lts__t_sector_hit_rate.pct", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
+    "smsp__warp_issue_stalled_wait_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
+    "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
+    "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct",
+    "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
+    "smsp__warp_issue_stalled_drain_per_warp_active.pct", "smsp__warp_issue_stalled_imc_miss_per_warp_active.pct",
+    "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "local_load", "local_store",
+]
+
+
+def ncu(*args):
+    return subprocess.run(["ncu", *args], capture_output=True, text=True).stdout
+
+
+def launch_shares(tag):
+    src = os.path.join(GO, "launches.csv")
+    if not os.path.exists(src):
+        return
+    os.makedirs(PR, exist_ok=True)
+    shutil.copy(src, os.path.join(PR, f"{tag}_launches.csv"))
+    txt = open(src).read()
+    start = txt.find('"ID"')
+    rows = list(csv.DictReader(io.StringIO(txt[start:])))
+    tot = defaultdict(float)
+    cnt = defaultdict(int)
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        name = re.sub(r"\(.*", "", r["Kernel Name"])
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
+        tot[name] += v
+        cnt[name] += 1
+    allms = sum(tot.values())
+    with open(os.path.join(PR, f"{tag}_launch_shares.md"), "w") as f:
+        f.write(f"# ncu launch list ({tag}): gpu__time_duration per kernel (cold-cache, serialised: compare SHARES)\n\n")
+        f.write("| kernel | launches | total ms | mean ms | share |\n|---|---|---|---|---|\n")
+        for k in sorted(tot, key=lambda k: -tot[k]):
+            f.write(f"| `{k}` | {cnt[k]} | {tot[k]:.3f} | {tot[k] / cnt[k]:.3f} | {100 * tot[k] / allms:.1f}% |\n")
+    print(open(os.path.join(PR, f"{tag}_launch_shares.md")).read())
+
+
+def full(tag):
+    for rep in sorted(glob.glob(os.path.join(GO, "prof_*.ncu-rep"))):
+        kname = os.path.basename(rep)[5:-8]
+        raw = ncu("-i", rep, "--page", "raw", "--csv")
+        rows = list(csv.reader(io.StringIO(raw)))
+        if len(rows) < 3:
+            print("no data in", rep)
+            continue
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        out = [f"# ncu --set full: {kname} ({tag})\n", "| metric | value | unit |", "|---|---|---|"]
+        for h, u, v in zip(hdr, units, vals):
+            if any(h == k or (k in ("local_load", "local_store") and k in h) for k in KEYS) or "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
+                out.append(f"| {h} | {v} | {u} |")
+        # source page: top stall lines
+        srcp = ncu("-i", rep, "--page", "source", "--csv")
+        srows = list(csv.reader(io.StringIO(srcp)))
+        if len(srows) > 2:
+            h = srows[0]
+            try:
+                i_src = h.index("Source")
+                i_samp = next(i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)" or "Sampling (All" in c)
+                agg = []
+                for r in srows[1:]:
+                    try:
+                        agg.append((float(r[i_samp].replace(",", "") or 0), r[i_src]))
+                    except Exception:
+                        pass
+                agg.sort(reverse=True)
+                tot = sum(a for a, _ in agg) or 1
+                out.append("\n## top sampled lines\n")
+                for a, s in agg[:25]:
+                    out.append(f"- {100 * a / tot:.1f}%  `{s.strip()[:140]}`")
+            except Exception as e:  # pragma: no cover
+                out.append(f"\n(source page not parsed: {e})")
+        path = os.path.join(PR, f"{tag}_{kname}.md")
+        open(path, "w").write("\n".join(out) + "\n")
+        print("wrote", path)
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    launch_shares(tag)
+    full(tag)
