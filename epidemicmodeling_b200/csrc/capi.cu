@@ -685,7 +685,7 @@ extern "C" int epi_pareto_batch(epi_ctx *c, const epi_pareto_args *a) {
     if (a->n_sets < 0 || a->n < 0) bad_arg("epi_pareto_batch: bad sizes");
     if (a->n_sets == 0 || a->n == 0) return;
     if (!a->J0 || !a->J1) bad_arg("epi_pareto_batch: J0 and J1 are required");
-    if ((size_t)a->n * 16 > 200 * 1024) bad_arg("epi_pareto_batch: n too large for one CTA's shared memory (max 12800)");
+    if ((size_t)a->n_sets * (size_t)a->n > 0x7fffffffull) bad_arg("epi_pareto_batch: more than 2^31 points");
     reset_phases(c);
     Call k(c, a->mem);
     const size_t tot = (size_t)a->n_sets * a->n;
@@ -695,8 +695,14 @@ extern "C" int epi_pareto_batch(epi_ctx *c, const epi_pareto_args *a) {
     p.on_front = k.out(a->on_front, tot);
     p.I_opt = k.out(a->I_opt, (size_t)a->n_sets);
     PhaseScope ph(c, "pareto");
-    launch_pareto(p, c->stream);
-    check_launch(c, 1);
+    if (a->n <= kParetoBruteMax) {
+      launch_pareto(p, c->stream);
+      check_launch(c, 1);
+    } else {
+      const size_t sb = pareto_sorted_scratch_bytes(a->n_sets, a->n);
+      void *scratch = k.dalloc(sb);
+      check_launch(c, launch_pareto_sorted(p, scratch, sb, c->stream));
+    }
     ph.end();
     k.flush();
     finish(c, a->mem);
@@ -718,7 +724,6 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         !a->Ps_final || !a->Q || !a->x0 || !a->weights || !a->J0 || !a->J1 || (a->T_hist > 0 && !a->newcases_hist))
       bad_arg("epi_sweep: a required array is null");
     if (a->u_knee && !a->I_opt) bad_arg("epi_sweep: u_knee needs I_opt");
-    if ((size_t)a->n_eps * 16 > 200 * 1024) bad_arg("epi_sweep: n_eps too large (max 12800)");
     reset_phases(c);
     const int M = 6, MM = 36, PF = 21, T = a->T, L = a->L, Tf = a->T - a->T_hist;
     const long long nR = a->n_regions, B = nR * a->n_eps;
@@ -834,8 +839,14 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       ParetoParams pp{};
       pp.n_sets = (int)nR; pp.n = a->n_eps; pp.J0 = J0; pp.J1 = J1; pp.on_front = on_front; pp.I_opt = I_opt;
       PhaseScope ph(c, "pareto");
-      launch_pareto(pp, c->stream);
-      check_launch(c, 1);
+      if (a->n_eps <= kParetoBruteMax) {
+        launch_pareto(pp, c->stream);
+        check_launch(c, 1);
+      } else {
+        const size_t sb = pareto_sorted_scratch_bytes((int)nR, a->n_eps);
+        void *scratch = shared.dalloc(sb);
+        check_launch(c, launch_pareto_sorted(pp, scratch, sb, c->stream));
+      }
       if (u_knee) {
         launch_gather_knee(u_fore_dev, I_opt, u_knee, (int)nR, a->n_eps, Tf, L, c->stream);
         check_launch(c, 1);

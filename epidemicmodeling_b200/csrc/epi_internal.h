@@ -120,6 +120,10 @@ struct ParetoParams {
   int *I_opt;
 };
 void launch_pareto(const ParetoParams &p, cudaStream_t st);
+// large point sets: sort-based evaluation of the same predicate (pareto_sorted.cu)
+constexpr int kParetoBruteMax = 8192;  // points per set up to which the O(n^2) CTA kernel is used
+size_t pareto_sorted_scratch_bytes(int n_sets, int n);
+int launch_pareto_sorted(const ParetoParams &p, void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 // gather the knee schedule: u_knee[r][t][j] = u_fore[t][j][r*n_eps + I_opt[r]]
 void launch_gather_knee(const double *u_fore, const int *I_opt, double *u_knee, int n_regions,

@@ -2,6 +2,8 @@
 // SI rollout, Pareto front + knee, knee-schedule gather (sm_100a, FP64,
 // --fmad=false).  One thread per trajectory; every per-step store of a warp is
 // a single coalesced 256-byte transaction (trajectory-minor layout).
+#include <type_traits>
+
 #include "epi_internal.h"
 #include "epi_device.cuh"
 
@@ -65,8 +67,111 @@ __global__ void __launch_bounds__(256) seirp_kernel(const __grid_constant__ Seir
   }
 }
 
+// ---------------------------------------------------------------------------
+// FULL-output variant: HBM-write bound (40 B per trajectory-step).  Writing each warp's
+// 256-byte row piece as it is produced scatters small writes over rows that are B*8
+// bytes apart (measured 20 % of the HBM roof, ncu r01).  Here a CTA of SB consecutive
+// trajectories stages TS steps x 5 compartments in shared memory and one thread hands
+// every (compartment, step) row -- SB*8 contiguous bytes -- to the TMA engine
+// (cp.async.bulk shared -> global), double buffered so the next stage is integrated
+// while the previous one drains.
+// ---------------------------------------------------------------------------
+EPI_DI void bulk_store_row(double *gdst, const double *ssrc, unsigned bytes) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+               : "memory");
+}
+
+template <int RATE_MODE, bool SAT, int SB, int TS>
+__global__ void __launch_bounds__(SB) seirp_staged_kernel(const __grid_constant__ SeirpParams P) {
+  extern __shared__ __align__(128) double stage_buf[];  // [2][5][TS][SB]
+  const int tid = threadIdx.x;
+  const long long blk0 = (long long)blockIdx.x * SB;
+  const int b = (int)(blk0 + tid);
+  const bool active = b < P.B;
+  const int nb = (P.B - blk0 < SB) ? (int)(P.B - blk0) : SB;
+  const int K = P.K;
+  const double dt = P.dt;
+  const size_t is = (size_t)P.ic.stride, rs = (size_t)P.rates.stride, os = (size_t)P.out.stride;
+  double S = 0, E = 0, I = 0, R = 0, Pd = 0;
+  double ae = 0, ai = 0, ka = 0, ro = 0, be = 0, mu = 0, ga = 0;
+  const double *__restrict__ rt = (RATE_MODE == EPI_RATES_SHARED_SERIES) ? P.rates_shared
+                                  : (active ? P.rates.p + P.rates.off + b : nullptr);
+  if (active) {
+    const double *__restrict__ ic = P.ic.p + P.ic.off + b;
+    S = ic[0]; E = ic[is]; I = ic[2 * is]; R = ic[3 * is]; Pd = ic[4 * is];
+    if (RATE_MODE == EPI_RATES_CONST) {
+      ae = rt[0]; ai = rt[rs]; ka = rt[2 * rs]; ro = rt[3 * rs]; be = rt[4 * rs]; mu = rt[5 * rs];
+      ga = rt[6 * rs];
+    }
+  }
+  double *__restrict__ gout = P.out.p + P.out.off + blk0;  // row (f, t) starts at gout[f*K*os + t*os]
+  const size_t KB = (size_t)K * os;
+  int stage = 0;
+  for (int t0 = 0; t0 < K; t0 += TS) {
+    double *buf = stage_buf + (size_t)stage * 5 * TS * SB;
+    // the bulk stores issued from this buffer two stages ago must have finished reading it
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncthreads();
+    const int nts = (K - t0 < TS) ? (K - t0) : TS;
+    for (int ts = 0; ts < nts; ++ts) {
+      const int t = t0 + ts;
+      buf[(0 * TS + ts) * SB + tid] = S; buf[(1 * TS + ts) * SB + tid] = E; buf[(2 * TS + ts) * SB + tid] = I;
+      buf[(3 * TS + ts) * SB + tid] = R; buf[(4 * TS + ts) * SB + tid] = Pd;
+      if (active && t + 1 < K) {  // :26  (only rate samples 0..K-2 are read)
+        if (RATE_MODE == EPI_RATES_SHARED_SERIES) {
+          const double *r = rt + t;
+          ae = r[0]; ai = r[(size_t)K]; ka = r[(size_t)2 * K]; ro = r[(size_t)3 * K];
+          be = r[(size_t)4 * K]; mu = r[(size_t)5 * K]; ga = r[(size_t)6 * K];
+        } else if (RATE_MODE == EPI_RATES_SERIES) {
+          const double *r = rt + (size_t)t * 7 * rs;
+          ae = r[0]; ai = r[rs]; ka = r[2 * rs]; ro = r[3 * rs]; be = r[4 * rs]; mu = r[5 * rs]; ga = r[6 * rs];
+        }
+        if (SAT) {
+          const double h = (tanh((I - P.i_0) / P.sigma) + 1.0) / 2.0;  // Saturated :27
+          be = (P.beta_s - P.beta_0) * h + P.beta_0;                    // :28
+          mu = (P.mu_s - P.mu_0) * h + P.mu_0;                          // :29
+        }
+        // :27-31 as MATLAB parses them (unary minus first, then left to right)
+        const double Sn = ((((-ae) * S) * E - (ai * S) * I) + ga * R) * dt + S;
+        const double En = (((((ae * S) * E) + ((ai * S) * I)) - ka * E) - ro * E) * dt + E;
+        const double In = ((ka * E - be * I) - mu * I) * dt + I;
+        const double Rn = ((be * I + ro * E) - ga * R) * dt + R;
+        const double Pn = (mu * I) * dt + Pd;
+        S = Sn; E = En; I = In; R = Rn; Pd = Pn;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy
+    __syncthreads();
+    if (tid == 0) {
+      for (int f = 0; f < 5; ++f)
+        for (int ts = 0; ts < nts; ++ts)
+          bulk_store_row(gout + (size_t)f * KB + (size_t)(t0 + ts) * os, buf + (f * TS + ts) * SB,
+                         (unsigned)nb * 8u);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    stage ^= 1;
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+constexpr int kSeirpSB = 256, kSeirpTS = 4;
+template <int RM, bool SAT>
+static bool seirp_launch_staged(const SeirpParams &p, cudaStream_t st) {
+  // TMA bulk copies need 16-byte aligned rows: even row stride/offset/length
+  if (p.out_mode != EPI_SEIRP_OUT_FULL || (p.B & 1) || (p.out.stride & 1) || (p.out.off & 1) ||
+      ((size_t)p.out.p & 15) || p.B < 4 * kSeirpSB)
+    return false;
+  const size_t smem = (size_t)2 * 5 * kSeirpTS * kSeirpSB * sizeof(double);
+  auto kern = seirp_staged_kernel<RM, SAT, kSeirpSB, kSeirpTS>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(p.B + kSeirpSB - 1) / kSeirpSB, kSeirpSB, smem, st>>>(p);
+  return true;
+}
+
 template <int RM, bool SAT>
 static void seirp_launch2(const SeirpParams &p, cudaStream_t st, int grid, int block) {
+  if (seirp_launch_staged<RM, SAT>(p, st)) return;
   if (p.out_mode == EPI_SEIRP_OUT_FULL) seirp_kernel<RM, SAT, true><<<grid, block, 0, st>>>(p);
   else seirp_kernel<RM, SAT, false><<<grid, block, 0, st>>>(p);
 }
@@ -171,7 +276,167 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   }
 }
 
+// ---------------------------------------------------------------------------
+// Staged variant for supplied schedules (BASELINE config 5): the [K][L][B] NPI array is
+// the only HBM stream (12 B or 96 B per trajectory-day).  Reading it one 32-byte (uint8)
+// or 256-byte (FP64) row piece per warp load reached 5 % of the HBM roof (ncu r01): rows
+// are B bytes apart, so every access opens a new DRAM page.  Here a CTA of SB consecutive
+// trajectories pulls TT days x L rows per stage into shared memory with TMA bulk copies
+// (cp.async.bulk global -> shared, mbarrier completion), double buffered: SB-byte /
+// SB*8-byte contiguous rows, fetched while the previous stage is being integrated.
+// ---------------------------------------------------------------------------
+EPI_DI void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+EPI_DI void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
+}
+EPI_DI void mbar_wait(unsigned long long *bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+EPI_DI void bulk_load_row(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          (unsigned)__cvta_generic_to_shared(sdst)),
+      "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+      : "memory");
+}
+
+template <int U_KIND, int SB, int TT>
+__global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constant__ RolloutParams P) {
+  using U = typename std::conditional<U_KIND == EPI_U_U8, unsigned char, double>::type;
+  extern __shared__ __align__(128) unsigned char stage_raw[];  // [2][TT][L][SB] of U
+  __shared__ unsigned long long bars[2];
+  const int tid = threadIdx.x;
+  const long long blk0 = (long long)blockIdx.x * SB;
+  const int b = (int)(blk0 + tid);
+  const bool active = b < P.B;
+  const int nb = (P.B - blk0 < SB) ? (int)(P.B - blk0) : SB;
+  const int K = P.K, L = P.L;
+  U *stage_u = reinterpret_cast<U *>(stage_raw);
+  const size_t stage_elems = (size_t)TT * L * SB;
+  const U *__restrict__ gu = reinterpret_cast<const U *>(P.u) + (size_t)P.u_off + blk0;
+  const size_t us = (size_t)P.u_stride;
+  const int n_stages = (K + TT - 1) / TT;
+
+  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  auto issue = [&](int sidx) {  // executed by warp 0
+    const int t0 = sidx * TT;
+    const int nt = (K - t0 < TT) ? (K - t0) : TT;
+    const int rows = nt * L;
+    unsigned long long *bar = &bars[sidx & 1];
+    U *dst = stage_u + (size_t)(sidx & 1) * stage_elems;
+    if (tid == 0) mbar_expect_tx(bar, (unsigned)((size_t)rows * nb * sizeof(U)));
+    __syncwarp();
+    for (int r = tid; r < rows; r += 32)
+      bulk_load_row(dst + (size_t)r * SB, gu + ((size_t)t0 * L + r) * us, (unsigned)(nb * sizeof(U)), bar);
+  };
+  if (tid < 32) {
+    issue(0);
+    if (n_stages > 1) issue(1);
+  }
+
+  const long long g = active ? (P.b0 + b) / P.G : 0;
+  const epi_model_params *__restrict__ prm = P.prm + g;
+  const double dt = prm->dt, beta = prm->beta, gamma = prm->gamma, bb = prm->b;
+  const double amin = prm->alpha_min, amax = prm->alpha_max;
+  double S = P.x0[3 * g + 0], I = P.x0[3 * g + 1], A = P.x0[3 * g + 2];
+  double sd_s = 0.0, sd_i = 0.0, sd_a = 0.0;
+  if (P.noise_std) { sd_s = P.noise_std[3 * g + 0]; sd_i = P.noise_std[3 * g + 1]; sd_a = P.noise_std[3 * g + 2]; }
+  const bool want_cost = P.J0.p != nullptr;
+  double ga[EPI_LMAX], um[EPI_LMAX];  // loop-invariant gamma*a(j), u_max(j)
+#pragma unroll
+  for (int j = 0; j < EPI_LMAX; ++j) {
+    ga[j] = (j < L) ? gamma * __ldg(&prm->a[j]) : 0.0;
+    um[j] = (j < L) ? __ldg(&prm->u_max[j]) : 0.0;
+  }
+  double a0 = want_cost && P.j0_prefix ? P.j0_prefix[g] : 0.0;
+  double a1 = want_cost && P.j1_prefix ? P.j1_prefix[g] : 0.0;
+  const size_t ns = (size_t)P.noise.stride;
+  const double *__restrict__ nz = (P.noise.p && active) ? P.noise.p + P.noise.off + b : nullptr;
+
+  for (int sidx = 0; sidx < n_stages; ++sidx) {
+    mbar_wait(&bars[sidx & 1], (unsigned)((sidx >> 1) & 1));
+    const U *__restrict__ su = stage_u + (size_t)(sidx & 1) * stage_elems + tid;
+    const int t0 = sidx * TT;
+    const int nt = (K - t0 < TT) ? (K - t0) : TT;
+    if (active) {
+      for (int tt = 0; tt < nt; ++tt) {
+        const int t = t0 + tt;
+        double dot = 0.0, cday = 0.0;
+        const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
+#pragma unroll
+        for (int j = 0; j < EPI_LMAX; ++j) {
+          if (j < L) {
+            const double uj = (double)su[(size_t)(tt * L + j) * SB];
+            const double d = um[j] - uj;
+            dot = (j == 0) ? ga[j] * d : fma(ga[j], d, dot);
+            if (wd) {
+              const double wu = __ldg(wd + j) * uj;
+              cday = (j == 0) ? wu : (cday + wu);
+            }
+          }
+        }
+        double n_s = 0.0, n_i = 0.0, n_a = 0.0;
+        if (nz) {
+          n_s = nz[((size_t)t * 3 + 0) * ns];
+          n_i = nz[((size_t)t * 3 + 1) * ns];
+          n_a = nz[((size_t)t * 3 + 2) * ns];
+        }
+        const double asi = (A * S) * I;
+        const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + n_s * sd_s)));
+        const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + n_i * sd_i)));
+        const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dot) + n_a * sd_a)));
+        S = Sn; I = In; A = An;
+        if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
+        if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
+        if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
+        if (want_cost) {
+          a0 += (S * I) * A;  // s.*i.*alpha (:493)
+          a1 += cday;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done reading this buffer
+    if (tid < 32 && sidx + 2 < n_stages) issue(sidx + 2);
+  }
+  if (want_cost && active) {
+    P.J0.p[P.J0.off + b] = a0 / (double)P.T_total;                        // NPICost.m:6
+    P.J1.p[P.J1.off + b] = a1 / (double)((size_t)L * (size_t)P.T_total);  // NPICost.m:10
+  }
+}
+
+template <int U_KIND>
+static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
+  constexpr int SB = 256;
+  constexpr int TT = (U_KIND == EPI_U_U8) ? 16 : 2;
+  const size_t esz = (U_KIND == EPI_U_U8) ? 1 : 8;
+  // TMA bulk copies need 16-byte aligned, 16-byte multiple rows
+  if (p.K < 1 || p.B < 8 * SB || (((size_t)p.B * esz) & 15) || (((size_t)p.u_stride * esz) & 15) ||
+      (((size_t)p.u_off * esz) & 15) || ((size_t)p.u & 15))
+    return false;
+  const size_t smem = (size_t)2 * TT * p.L * SB * esz;
+  auto kern = rollout_staged_kernel<U_KIND, SB, TT>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  kern<<<(p.B + SB - 1) / SB, SB, smem, st>>>(p);
+  return true;
+}
+
 void launch_rollout(const RolloutParams &p, cudaStream_t st) {
+  if (p.u_kind == EPI_U_F64 && rollout_launch_staged<EPI_U_F64>(p, st)) return;
+  if (p.u_kind == EPI_U_U8 && rollout_launch_staged<EPI_U_U8>(p, st)) return;
   const int block = 128;
   const int grid = (p.B + block - 1) / block;
   if (p.u_kind == EPI_U_F64) rollout_kernel<EPI_U_F64><<<grid, block, 0, st>>>(p);

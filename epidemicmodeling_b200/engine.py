@@ -9,6 +9,7 @@ torch is plumbing only (device memory, streams, torch.distributed); every
 computation happens inside libepi_b200.so.  No CPU fallback exists.
 """
 import ctypes as C
+import sys
 
 import numpy as np
 
@@ -82,8 +83,7 @@ class Engine:
     def __del__(self):
         # never call into CUDA while the interpreter (and the CUDA runtime with it) is
         # being torn down: api.get_engine() registers an atexit close for the shared engine
-        import sys
-        if sys.is_finalizing():
+        if sys is None or sys.is_finalizing():
             return
         try:
             self.close()

@@ -115,10 +115,12 @@ def test_sialpha_controlled_signature(engine, noisy):
         assert_bits(got[0], g["s"]); assert_bits(got[1], g["i"]); assert_bits(got[2], g["alpha"])
 
 
-@pytest.mark.parametrize("u_kind", ["f64", "u8"])
-def test_rollout_cost_batch(engine, u_kind):
-    """BASELINE config 5 shape, small: regions x random schedules x 45 days with NPICost fused."""
-    nR, nS, Kn, L = 3, 257, 45, 12
+@pytest.mark.parametrize("u_kind,nS", [("f64", 257), ("u8", 257), ("f64", 1024), ("u8", 1024), ("u8", 1000)])
+def test_rollout_cost_batch(engine, u_kind, nS):
+    """BASELINE config 5 shape, small: regions x random schedules x 45 days with NPICost fused.
+    nS = 1024 takes the TMA-staged kernel (aligned rows), 257 / 1000(u8: rows not 16-byte
+    multiples) the plain one; 45 days = ragged last time tile."""
+    nR, Kn, L = 3, 45, 12
     reg = syn.load_regions(nR)
     rng = np.random.default_rng(21)
     B = nR * nS
@@ -178,6 +180,14 @@ def test_pareto_front(engine):
     for r in range(17):
         wm, wi = o.pareto(J0[r], J1[r])
         assert np.array_equal(m[r].astype(bool), wm) and io[r] == wi, r
+    # the sort-based path (n > 8192) against the O(n^2) oracle, with ties, NaN and +-0 keys
+    n = 9000
+    K0, K1 = np.round(rng.random((3, n)), 3), np.round(rng.random((3, n)), 3)   # many exact ties
+    K0[0, :5] = np.nan; K1[0, 5:9] = np.nan; K0[1, 10] = -0.0; K0[1, 11] = 0.0; K0[2, 7] = np.inf
+    ms, ios = engine.pareto(K0, K1)
+    for r in range(3):
+        wm, wi = o.pareto(K0[r], K1[r])
+        assert np.array_equal(ms[r].astype(bool), wm) and ios[r] == wi, ("sorted path", r)
     # idempotence at a size the O(n^2) oracle would not like: front(front) == front
     J0b, J1b = rng.random((1, 12000)), rng.random((1, 12000))
     mb, _ = engine.pareto(J0b, J1b)

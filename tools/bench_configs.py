@@ -1,0 +1,151 @@
+"""Secondary measurements for the other BASELINE.json configs (2, 3, 5) on one B200.
+bench.py carries the headline (config 4); this script records the remaining kernels'
+throughput and roofline fractions into gpurun_out/configs.jsonl (copied to profiles/).
+
+    python tools/bench_configs.py [--scale 1.0]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from epidemicmodeling_b200 import _capi as K  # noqa: E402
+from epidemicmodeling_b200 import synthetic as syn, workloads as wl  # noqa: E402
+from epidemicmodeling_b200.engine import Engine, pack_params, params_to_device  # noqa: E402
+
+HBM = 6550.1
+try:
+    HBM = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    a = ap.parse_args()
+    eng = Engine(0)
+    eng.use_torch_stream()
+    fp64 = eng.fp64_probe(4096)
+    out = []
+    dev = "cuda:0"
+
+    # ---- config 2: SEIRP ensemble, 1M x 365 days
+    B, Kn = int(1_000_000 * a.scale), 365
+    rates, ic = syn.seirp_ensemble(B)
+    rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
+    for mode, name in ((K.SEIRP_OUT_FULL, "full"), (K.SEIRP_OUT_FINAL, "final")):
+        ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, out_mode=mode))
+        steps = B * (Kn - 1)
+        rec = {"config": 2, "kernel": f"seirp[{name}]", "B": B, "K": Kn, "ms": ms, "steps_per_s": steps / ms * 1e3,
+               "hbm_gbs": (40.0 * B * Kn / ms * 1e3 / 1e9) if mode == K.SEIRP_OUT_FULL else 0.0,
+               "fp64_tflops": 37.0 * steps / ms * 1e3 / 1e12}
+        rec["hbm_frac"] = rec["hbm_gbs"] / HBM
+        rec["fp64_frac"] = rec["fp64_tflops"] / fp64
+        out.append(rec)
+    del rd, icd
+    sat = dict(beta_0=0.1, beta_s=0.01, mu_0=0.02, mu_s=0.2, sigma=1.0, i_0=0.1)
+    rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
+    ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, saturated=sat, out_mode=K.SEIRP_OUT_FINAL))
+    out.append({"config": 2, "kernel": "seirp_saturated[final]", "B": B, "K": Kn, "ms": ms,
+                "steps_per_s": B * (Kn - 1) / ms * 1e3})
+    del rd, icd
+    torch.cuda.empty_cache()
+
+    # ---- config 3: SI-alpha EKF + smoother, 236 regions x replicates x 400 days
+    nR, nRep, T = 236, int(10_000 * a.scale), 400
+    inp = syn.sweep_inputs(n_regions=nR, T_hist=T, T_fore=0)
+    b = wl.fixed_input_batch(inp)
+    Bt = nR * nRep
+    clean = torch.from_numpy(np.stack([r["x"] for r in inp])).to(dev)            # [nR,T]
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.empty((T, Bt), dtype=torch.float64, device=dev)
+    for r in range(nR):
+        x[:, r * nRep:(r + 1) * nRep] = torch.clamp_min(
+            clean[r][:, None] * (1.0 + 0.05 * torch.randn((T, nRep), dtype=torch.float64, device=dev, generator=g)), 0.0)
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    args = (params_to_device(b["prm"], dev), t(b["u"]), x, t(b["R"]), t(b["Q"]), t(b["s_init"]), t(b["Ps_init"]),
+            t(b["s_final"]), t(b["Ps_final"]))
+    kw = dict(B=Bt, T=T, L=b["L"], G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=1.0,
+              gamma=b["gamma"], W=b["W"], outputs=("S_SMOOTH",))
+    holder = {}
+
+    eng.set_scratch_limit(48 << 30)   # keep the waves' scratch in the pool instead of fighting torch's allocator
+
+    def run3():
+        holder.clear()
+        holder["o"] = eng.ekf_eks(K.MODEL_SIALPHA, *args, **kw)
+    ms = timed(run3, reps=3, warm=1)
+    eng.set_scratch_limit(0)
+    kt = eng.last_kernel_times()
+    units = Bt * T
+    out.append({"config": 3, "kernel": "ekf_eks<3> lean (S_SMOOTH out)", "B": Bt, "T": T, "ms": ms,
+                "trajectory_days_per_s": units / ms * 1e3, "kernel_ms": kt, "kernel_ms_sum": sum(kt.values()),
+                "hbm_gbs_algorithmic(616B)": 616.0 * units / ms * 1e3 / 1e9,
+                "hbm_frac": 616.0 * units / ms * 1e3 / 1e9 / HBM,
+                "fp64_frac(818flop)": 818.0 * units / ms * 1e3 / 1e12 / fp64})
+    holder.clear()
+    del x, args
+    torch.cuda.empty_cache()
+
+    # ---- config 5: random-NPI Monte-Carlo scoring, 236 regions x 100k schedules x 120 days (uint8 NPIs)
+    nS, Kn, L = int(100_000 * a.scale), 120, 12
+    reg = syn.load_regions(nR)
+    Bm = nR * nS
+    umax = torch.tensor(reg["npi_max"], dtype=torch.float64, device=dev)
+    u8 = torch.empty((Kn, L, Bm), dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    for j in range(L):  # TrainPredictPrescribeNPI.m:500-510: first half constant in time, second half per day
+        hi = int(reg["npi_max"][j]) + 1
+        per_day = torch.randint(0, hi, (Kn, Bm), dtype=torch.uint8, device=dev, generator=g)
+        const = torch.randint(0, hi, (1, Bm), dtype=torch.uint8, device=dev, generator=g)
+        first_half = (torch.arange(Bm, device=dev) % nS) < (nS // 2)
+        u8[:, j, :] = torch.where(first_half[None, :], const.expand(Kn, Bm), per_day)
+        del per_day, const
+    prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                            alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
+    x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)]))
+    w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)]))
+    j0p, j1p = torch.zeros(nR, dtype=torch.float64, device=dev), torch.zeros(nR, dtype=torch.float64, device=dev)
+    prmd = params_to_device(prm, dev)
+
+    def run5():
+        holder["o"] = eng.rollout_cost(prmd, x0, u8, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
+                                       T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w)
+    ms = timed(run5, reps=3, warm=1)
+    units = Bm * Kn
+    out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
+                "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
+                "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
+
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "w") as f:
+        for r in out:
+            r["hbm_peak_gbs"], r["fp64_peak_tflops_measured"] = HBM, fp64
+            f.write(json.dumps(r) + "\n")
+            print(json.dumps(r))
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
