@@ -45,7 +45,7 @@ KERNEL_ALGO = {                   # per trajectory-day: (algorithmic bytes, cano
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--regions", type=int, default=236)
@@ -309,7 +309,7 @@ def main():
                 send[1].copy_(torch.from_numpy(hout["J1"]), non_blocking=True)
                 dist.all_gather_into_tensor(gathered.view(-1), send.view(-1))
 
-        for _ in range(2):
+        for _ in range(3):
             step_host()
         fence()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -39,6 +40,11 @@ struct epi_ctx {
   long long launches = 0;
   std::vector<Phase> phases;       // of the most recent batched call
   std::vector<cudaEvent_t> ev_pool;
+  // context-owned device memory: staging/scratch blocks are cached here between calls, so a
+  // repeated call (a sweep per step, a MEX call per region) never pays cudaMalloc again.  All
+  // work of a context is enqueued on ONE stream, so recycling a block is stream-ordered.
+  std::multimap<size_t, void *> free_blocks;
+  size_t cached_bytes = 0;
 };
 
 namespace {
@@ -83,12 +89,51 @@ struct PhaseScope {
   }
 };
 
+void trim_cache(epi_ctx *c) {
+  if (c->free_blocks.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto &kv : c->free_blocks) cudaFree(kv.second);
+  c->free_blocks.clear();
+  c->cached_bytes = 0;
+}
+void *ctx_alloc(epi_ctx *c, size_t *bytes_io) {
+  size_t bytes = (*bytes_io + 511) & ~(size_t)511;
+  if (bytes == 0) bytes = 512;
+  *bytes_io = bytes;
+  auto it = c->free_blocks.lower_bound(bytes);
+  if (it != c->free_blocks.end() && it->first <= bytes + bytes / 4 + 65536) {
+    void *p = it->second;
+    *bytes_io = it->first;
+    c->cached_bytes -= it->first;
+    c->free_blocks.erase(it);
+    return p;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {  // give the cache back and retry once
+    cudaGetLastError();
+    trim_cache(c);
+    e = cudaMalloc(&p, bytes);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char buf[256];
+    snprintf(buf, sizeof buf, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    throw EpiError{e == cudaErrorMemoryAllocation ? EPI_ERR_NOMEM : EPI_ERR_CUDA, buf};
+  }
+  return p;
+}
+void ctx_free(epi_ctx *c, void *p, size_t bytes) {
+  c->free_blocks.emplace(bytes, p);
+  c->cached_bytes += bytes;
+}
+
 // one batched call (or one wave of it): owns the staging buffers it allocated
 // and the list of device->host copies to issue once the kernels are enqueued.
 struct Call {
   epi_ctx *c;
   int mem;
-  std::vector<void *> dev;
+  std::vector<std::pair<void *, size_t>> dev;
   struct Copy { void *dst; const void *src; size_t dpitch, spitch, width, height; };
   std::vector<Copy> pend;
 
@@ -97,14 +142,12 @@ struct Call {
   Call(const Call &) = delete;
 
   void *dalloc(size_t bytes) {
-    void *p = nullptr;
-    if (bytes == 0) bytes = 8;
-    CK(cudaMallocAsync(&p, bytes, c->stream));
-    dev.push_back(p);
+    void *p = ctx_alloc(c, &bytes);
+    dev.emplace_back(p, bytes);
     return p;
   }
   void release() {
-    for (void *p : dev) cudaFreeAsync(p, c->stream);
+    for (auto &pb : dev) ctx_free(c, pb.first, pb.second);
     dev.clear();
   }
   // whole-array input of n elements (per-group tables etc.)
@@ -175,15 +218,7 @@ size_t scratch_budget(epi_ctx *c) {
   if (c->scratch_limit) return c->scratch_limit;
   size_t fr = 0, tot = 0;
   CK(cudaMemGetInfo(&fr, &tot));
-  // memory cached in the stream-ordered pool counts as "used" in cudaMemGetInfo
-  cudaMemPool_t pool;
-  unsigned long long reserved = 0, used = 0;
-  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
-    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
-  }
-  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0);
-  return (size_t)(0.6 * (double)avail);
+  return (size_t)(0.6 * (double)(fr + c->cached_bytes));  // blocks cached by this context are reusable
 }
 
 long long wave_size(long long B, size_t bytes_per_traj, size_t budget) {
@@ -252,12 +287,6 @@ extern "C" int epi_create(int device, epi_ctx **out) {
     return EPI_ERR_CUDA;
   }
   c->stream = c->own_stream;
-  // keep freed staging/scratch memory cached in the stream-ordered pool
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    unsigned long long thr = ~0ull;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
   *out = c;
   g_create_err.clear();
   return EPI_OK;
@@ -268,6 +297,7 @@ extern "C" void epi_destroy(epi_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   reset_phases(c);
+  trim_cache(c);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -277,7 +307,12 @@ extern "C" const char *epi_last_error(const epi_ctx *c) { return c ? c->err.c_st
 
 extern "C" int epi_set_stream(epi_ctx *c, void *s) {
   if (!c) return EPI_ERR_ARG;
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  cudaStream_t ns = s ? (cudaStream_t)s : c->own_stream;
+  if (ns != c->stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);  // cached blocks are recycled in stream order: drain the old stream
+    c->stream = ns;
+  }
   return EPI_OK;
 }
 

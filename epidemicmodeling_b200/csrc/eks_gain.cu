@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 #pragma unroll
       for (int q = 0; q < MM; ++q) Jm.v[q] = 0.0;  // :213
     } else {
-      rank = pinv_sym<M>(Pn, X);
+      VRegs<M> v;  // eigenvectors in registers (a shared-memory V was measured slower: 9.1 vs 8.0 ms)
+      rank = pinv_sym<M>(Pn, X, v);
       Mat<M, true> Pp;
       tape_load_cov<M, true, TILED, PACKED>(Pp, tPp, tPp.at_day(pos));
       Mat<M, false> PAt;

@@ -373,39 +373,56 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
     const int t0 = sidx * TT;
     const int nt = (K - t0 < TT) ? (K - t0) : TT;
     if (active) {
-      for (int tt = 0; tt < nt; ++tt) {
-        const int t = t0 + tt;
-        double dot = 0.0, cday = 0.0;
-        const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
+      // the input term and the day's weighted cost do not depend on the state: evaluate them
+      // for DQ days at once (independent FMA chains = instruction-level parallelism), then run
+      // the DQ strictly sequential state updates
+      constexpr int DQ = 4;
+      for (int tq = 0; tq < nt; tq += DQ) {
+        double dotq[DQ], cq[DQ];
 #pragma unroll
-        for (int j = 0; j < EPI_LMAX; ++j) {
-          if (j < L) {
-            const double uj = (double)su[(size_t)(tt * L + j) * SB];
-            const double d = um[j] - uj;
-            dot = (j == 0) ? ga[j] * d : fma(ga[j], d, dot);
-            if (wd) {
-              const double wu = __ldg(wd + j) * uj;
-              cday = (j == 0) ? wu : (cday + wu);
+        for (int q = 0; q < DQ; ++q) {
+          dotq[q] = 0.0; cq[q] = 0.0;
+          const int tt = tq + q;
+          if (tt < nt) {
+            const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + (t0 + tt)) * L : nullptr;
+#pragma unroll
+            for (int j = 0; j < EPI_LMAX; ++j) {
+              if (j < L) {
+                const double uj = (double)su[(size_t)(tt * L + j) * SB];
+                const double d = um[j] - uj;
+                dotq[q] = (j == 0) ? ga[j] * d : fma(ga[j], d, dotq[q]);
+                if (wd) {
+                  const double wu = __ldg(wd + j) * uj;
+                  cq[q] = (j == 0) ? wu : (cq[q] + wu);
+                }
+              }
             }
           }
         }
-        double n_s = 0.0, n_i = 0.0, n_a = 0.0;
-        if (nz) {
-          n_s = nz[((size_t)t * 3 + 0) * ns];
-          n_i = nz[((size_t)t * 3 + 1) * ns];
-          n_a = nz[((size_t)t * 3 + 2) * ns];
-        }
-        const double asi = (A * S) * I;
-        const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + n_s * sd_s)));
-        const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + n_i * sd_i)));
-        const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dot) + n_a * sd_a)));
-        S = Sn; I = In; A = An;
-        if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
-        if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
-        if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
-        if (want_cost) {
-          a0 += (S * I) * A;  // s.*i.*alpha (:493)
-          a1 += cday;
+#pragma unroll
+        for (int q = 0; q < DQ; ++q) {
+          const int tt = tq + q;
+          if (tt < nt) {
+            const int t = t0 + tt;
+            double n_s = 0.0, n_i = 0.0, n_a = 0.0;
+            if (nz) {
+              n_s = nz[((size_t)t * 3 + 0) * ns];
+              n_i = nz[((size_t)t * 3 + 1) * ns];
+              n_a = nz[((size_t)t * 3 + 2) * ns];
+            }
+            const double asi = (A * S) * I;
+            const double Sn = mmax(0.0, mmin(1.0, S - dt * (asi + n_s * sd_s)));
+            const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + n_i * sd_i)));
+            const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dotq[q]) + n_a * sd_a)));
+            S = Sn; I = In; A = An;
+            if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
+            if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
+            if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
+            if (want_cost) {
+              a0 += (S * I) * A;  // s.*i.*alpha (:493)
+              a1 += cq[q];
+            }
+          }
         }
       }
     }

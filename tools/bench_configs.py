@@ -138,6 +138,12 @@ def main():
                 "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
                 "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
 
+    J0, J1 = holder["o"]["J0"].view(nR, nS), holder["o"]["J1"].view(nR, nS)
+    ms = timed(lambda: holder.__setitem__("p", eng.pareto(J0, J1)), reps=3, warm=1)
+    mask, iopt = holder["p"]
+    out.append({"config": 5, "kernel": "pareto[sorted]", "n_sets": nR, "n": nS, "ms": ms,
+                "points_per_s": nR * nS / ms * 1e3, "front_sizes_mean": float(mask.sum(dim=1).double().mean().item())})
+
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "w") as f:
         for r in out:
