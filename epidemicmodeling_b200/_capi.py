@@ -85,7 +85,7 @@ class SweepArgs(C.Structure):
                 ("Ps_final", _dp), ("Q", _dp), ("beta_ekf", C.c_double), ("gamma_ekf", C.c_double),
                 ("W", C.c_int), ("x0", _dp), ("newcases_hist", _dp), ("weights", _dp),
                 ("noise_std", _dp), ("noise", _dp), ("J0", _dp), ("J1", _dp), ("on_front", _dp),
-                ("I_opt", _dp), ("u_knee", _dp), ("u_fore", _dp), ("P_first", _dp)]
+                ("I_opt", _dp), ("u_knee", _dp), ("u_fore", _dp), ("P_first", _dp), ("lean", C.c_int)]
 
 
 # every symbol include/epi_b200.h declares: name -> (restype, argtypes)

@@ -759,6 +759,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         !a->Ps_final || !a->Q || !a->x0 || !a->weights || !a->J0 || !a->J1 || (a->T_hist > 0 && !a->newcases_hist))
       bad_arg("epi_sweep: a required array is null");
     if (a->u_knee && !a->I_opt) bad_arg("epi_sweep: u_knee needs I_opt");
+    if (a->lean && a->P_first) bad_arg("epi_sweep: P_first needs the full smoother (lean = 0)");
     reset_phases(c);
     const int M = 6, MM = 36, PF = 21, T = a->T, L = a->L, Tf = a->T - a->T_hist;
     const long long nR = a->n_regions, B = nR * a->n_eps;
@@ -802,7 +803,11 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       check_launch(c, 1);
       ph.end();
     }
-    size_t per = (size_t)(T - 1) * MM * 8 + (size_t)2 * T * M * 8 + (size_t)2 * T * PF * 8 + (size_t)2 * T * 8;
+    // lean: the smoother is needed from the first day to optimise on (k0 = T_hist); keep at least
+    // the last day so the terminal condition has its tape page
+    const int k0 = a->lean ? (a->T_hist < T - 1 ? a->T_hist : T - 1) : 0;
+    const int Tn = T - k0;  // days of tape kept
+    size_t per = (size_t)(Tn > 1 ? Tn - 1 : 1) * MM * 8 + (size_t)2 * Tn * M * 8 + (size_t)2 * Tn * PF * 8 + (size_t)2 * T * 8;
     if (host && a->noise) per += (size_t)Tf * 24;
     if (host && a->P_first) per += (size_t)MM * 8;
     const long long Bw = wave_size(B, per, scratch_budget(c));
@@ -821,12 +826,13 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       p.s_init_g = s_init; p.Ps_init_g = Ps_init; p.s_final_g = s_final; p.Ps_final_g = Ps_final;
       p.v_bar = 0.0; p.beta = a->beta_ekf; p.gamma = a->gamma_ekf;
       p.tiled = 1;
+      p.k0 = k0;
       p.dot_grp = dot_grp; p.cost_grp = cost_grp;
-      p.S_MINUS = w.scratch_tiled((size_t)T * M, nb);
-      p.S_PLUS = w.scratch_tiled((size_t)T * M, nb);
-      p.P_MINUS = w.scratch_tiled((size_t)T * PF, nb);
-      p.P_PLUS = w.scratch_tiled((size_t)T * PF, nb);
-      p.J = w.scratch_tiled((size_t)(T > 1 ? T - 1 : 1) * MM, nb);
+      p.S_MINUS = w.scratch_tiled((size_t)Tn * M, nb);
+      p.S_PLUS = w.scratch_tiled((size_t)Tn * M, nb);
+      p.P_MINUS = w.scratch_tiled((size_t)Tn * PF, nb);
+      p.P_PLUS = w.scratch_tiled((size_t)Tn * PF, nb);
+      p.J = w.scratch_tiled((size_t)(Tn > 1 ? Tn - 1 : 1) * MM, nb);
       p.dot_day = w.scratch_tiled(T, nb);
       p.cost_day = w.scratch_tiled(T, nb);
       p.weights = wts;
@@ -839,7 +845,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         check_launch(c, 1);
         ph.end();
       }
-      if (T > 1) {
+      if (Tn > 1) {
         PhaseScope ph(c, "eks_gain");
         launch_eks_gain(p, c->stream);
         check_launch(c, 1);
@@ -852,6 +858,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         ph.end();
       }
       RolloutParams r{};
+      r.hist_cost_grp = a->lean ? cost_grp : nullptr;
       r.B = (int)nb; r.K = Tf; r.L = L; r.G = a->n_eps; r.b0 = b0;
       r.prm = prm; r.x0 = x0; r.noise_std = nstd;
       r.u_kind = 2;

@@ -22,13 +22,15 @@ struct Tape {
   EPI_DI double *at_day(int t) const { return p + (size_t)t * day; }
   EPI_DI size_t f(int field) const { return TILED ? (size_t)field * 32 : (size_t)field * S; }
 };
+// `days` = number of days the array holds, `t0` = absolute index of its first day (lean
+// sweeps keep only the days the smoother needs); at_day() takes absolute day indices.
 template <bool TILED>
-EPI_DI Tape<TILED> make_tape(const TArr &a, int F, int T, int b) {
+EPI_DI Tape<TILED> make_tape(const TArr &a, int F, int days, int b, int t0 = 0) {
   Tape<TILED> t;
   if (TILED) {
-    t.p = a.p + ((size_t)(b >> 5) * (size_t)T * (size_t)F) * 32 + (size_t)(b & 31);
     t.S = 32;
     t.day = (size_t)F * 32;
+    t.p = a.p + ((size_t)(b >> 5) * (size_t)days * (size_t)F) * 32 + (size_t)(b & 31) - (size_t)t0 * t.day;
   } else {
     t.p = a.p + (size_t)a.off + (size_t)b;
     t.S = (size_t)a.stride;

@@ -77,9 +77,11 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
   const ModelConsts mc = load_consts(in.prm);
   const int T = P.T, L = P.L, W = P.W;
   const double gamma = P.gamma, beta = P.beta, v_bar = P.v_bar, eps = in.eps;
+  const InvDiv by_gamma = make_invdiv(gamma);
 
-  const Tape<TILED> tSm = make_tape<TILED>(P.S_MINUS, M, T, b), tSp = make_tape<TILED>(P.S_PLUS, M, T, b);
-  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T, b), tPp = make_tape<TILED>(P.P_PLUS, PF, T, b);
+  const int k0 = P.k0;  // lean sweeps: days before k0 are never read by the smoother
+  const Tape<TILED> tSm = make_tape<TILED>(P.S_MINUS, M, T - k0, b, k0), tSp = make_tape<TILED>(P.S_PLUS, M, T - k0, b, k0);
+  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T - k0, b, k0), tPp = make_tape<TILED>(P.P_PLUS, PF, T - k0, b, k0);
 
   double s[M];
   Mat<M, SYM> Pm;  // P(k|k-1)
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
   for (int k = 0; k < T; ++k) {
     const int pos = REV ? (T - 1 - k) : k;
     // :100-101 store the a-priori estimate
-    {
+    if (pos >= k0) {
       double *__restrict__ d = tSm.at_day(pos);
 #pragma unroll
       for (int i = 0; i < M; ++i) d[tSm.f(i)] = s[i];
@@ -137,8 +139,9 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
         CP[j] = fma(C[2], Pm(2, j), fma(C[1], Pm(1, j), C[0] * Pm(0, j)));
       const double S0 = fma(CP[2], C[2], fma(CP[1], C[1], CP[0] * C[0]));
       const double denom = S0 + gamma * Rk;  // :124 (+ Gsp + Gvp = 0)
+      const InvDiv by_denom = make_invdiv(denom);
 #pragma unroll
-      for (int i = 0; i < M; ++i) K[i] = PCt[i] / denom;
+      for (int i = 0; i < M; ++i) K[i] = div_by(PCt[i], by_denom);
       double Mx[M][3];  // I - K*C, columns 0..2 (columns 3.. are identity)
 #pragma unroll
       for (int i = 0; i < M; ++i)
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < M; ++i)
 #pragma unroll
-          for (int j = 0; j < M; ++j) Pp.at(i, j) = MP(i, j) / gamma;  // legacy :64
+          for (int j = 0; j < M; ++j) Pp.at(i, j) = div_by(MP(i, j), by_gamma);  // legacy :64
       } else {
         // :127 Joseph form, :138 symmetrisation
 #pragma unroll
@@ -168,8 +171,8 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
             if (j >= 3) mij = mij + MP(i, j);
             double mji = fma(MP(j, 2), Mx[i][2], fma(MP(j, 1), Mx[i][1], MP(j, 0) * Mx[i][0]));
             if (i >= 3) mji = mji + MP(j, i);
-            const double pij = (mij + (K[i] * Rk) * K[j]) / gamma;
-            const double pji = (mji + (K[j] * Rk) * K[i]) / gamma;
+            const double pij = div_by(mij + (K[i] * Rk) * K[j], by_gamma);
+            const double pji = div_by(mji + (K[j] * Rk) * K[i], by_gamma);
             Pp.at(i, j) = (pij + pji) / 2.0;
           }
       }
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
     for (int i = 0; i < M; ++i) s[i] = sn[i];
 
     // :167-169
-    {
+    if (pos >= k0) {
       double *__restrict__ d = tSp.at_day(pos);
 #pragma unroll
       for (int i = 0; i < M; ++i) d[tSp.f(i)] = sp[i];

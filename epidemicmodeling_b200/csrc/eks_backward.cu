@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
   const bool want_cost = P.cost_day.p != nullptr;
   const double *wts = want_cost ? P.weights + (size_t)g * T * L : nullptr;
 
-  const Tape<TILED> tSm = make_tape<TILED>(P.S_MINUS, M, T, b), tSp = make_tape<TILED>(P.S_PLUS, M, T, b);
-  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T, b), tPp = make_tape<TILED>(P.P_PLUS, PF, T, b);
-  const Tape<true> tJ = make_tape<true>(P.J, MM, T > 1 ? T - 1 : 1, b);
+  const int k0 = P.k0;  // lean sweeps: the recursion stops at the first day whose schedule is needed
+  const Tape<TILED> tSm = make_tape<TILED>(P.S_MINUS, M, T - k0, b, k0), tSp = make_tape<TILED>(P.S_PLUS, M, T - k0, b, k0);
+  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T - k0, b, k0), tPp = make_tape<TILED>(P.P_PLUS, PF, T - k0, b, k0);
+  const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1 - k0 > 0 ? T - 1 - k0 : 1, b, k0);
   const Tape<true> tDot = make_tape<true>(P.dot_day, 1, T, b), tCost = make_tape<true>(P.cost_day, 1, T, b);
 
   // writes the schedule of day `pos` implied by state `s5` (and the per-day scalars of the sweep)
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
   };
 
   BwdDay<M> cur;
-  if (!WANT_P && T >= 2) load_day(T - 2, cur);
+  if (!WANT_P && T - 2 >= k0) load_day(T - 2, cur);
 #pragma unroll 1
-  for (int k = T - 2; k >= 0; --k) {  // :204
+  for (int k = T - 2; k >= k0; --k) {  // :204
     const int pos = REV ? (T - 1 - k) : k;
     const int posn = REV ? (T - 2 - k) : (k + 1);
     if (WANT_P) load_day(k, cur);
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
     }
     // the tape page of this day is consumed: start streaming the previous day's page into
     // the same registers now, so its HBM latency overlaps the rest of this iteration
-    if (!WANT_P && k > 0) load_day(k - 1, cur);
+    if (!WANT_P && k > k0) load_day(k - 1, cur);
     state_margins<MODEL>(mc, sk);  // :221
     if (WANT_P) {
       Mat<M, SYM> Pp, Pn;

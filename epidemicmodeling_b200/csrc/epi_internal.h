@@ -48,7 +48,9 @@ struct EkfParams {
   int tiled;                       // 1: all four tape arrays are library scratch in the tile layout
                                    //    [b/32][T][F][32] (ekf_common.cuh); P pages of the generic
                                    //    models then hold the packed upper triangle (F = m(m+1)/2)
-  TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1][m*m][32]
+  int k0;                          // first day the smoother needs (0 = all).  Lean sweeps (tiled only):
+                                   // the tape holds days k0..T-1, gains/backward run for k >= k0
+  TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1-k0][m*m][32]
   const double *dot_grp;           // per group [T]: input term of days without NaN inputs (NaN = per trajectory)
   const double *cost_grp;          // per group [T]: that day's sum_j w*u (sweep), or null
   // optional outputs
@@ -92,6 +94,7 @@ struct RolloutParams {
   const double *j0_prefix, *j1_prefix, *w;    // per group
   const double *newcases_hist;    // sweep: per group [T_hist] (summed in-kernel)
   const double *dot_day, *cost_day;  // sweep: tiled [b/32][T_total][1][32] of this wave
+  const double *hist_cost_grp;       // lean sweep: per group [T_total] day costs of the (given) history
   TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);

@@ -217,7 +217,13 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     if (U_KIND == 2) {
       const double *nh = P.newcases_hist + (size_t)g * P.T_hist;
       for (int t = 0; t < P.T_hist; ++t) a0 += nh[t];
-      for (int t = 0; t < P.T_hist; ++t) a1 += costp[(size_t)t * cs];
+      if (P.hist_cost_grp) {  // lean sweep: the history is given, its day costs are per group
+        const double *hc = P.hist_cost_grp + (size_t)g * P.T_total;
+        // (the last day of the run is never a "given" day: u_opt_smooth(:,T) = 0, written by eks_backward)
+        for (int t = 0; t < P.T_hist; ++t) a1 += (t == P.T_total - 1) ? costp[(size_t)t * cs] : hc[t];
+      } else {
+        for (int t = 0; t < P.T_hist; ++t) a1 += costp[(size_t)t * cs];
+      }
     } else {
       a0 = P.j0_prefix ? P.j0_prefix[g] : 0.0;
       a1 = P.j1_prefix ? P.j1_prefix[g] : 0.0;

@@ -357,7 +357,7 @@ class Engine:
     def sweep(self, prm, eps, u, x, R, s_init, Ps_init, s_final, Ps_final, Q, x0, newcases_hist,
               weights, *, n_regions, T, T_hist, L, beta_ekf=1.0, gamma_ekf=0.995, W=21,
               noise_std=None, noise=None, want_front=True, want_u_knee=False, want_u_fore=False,
-              want_P_first=False, out=None):
+              want_P_first=False, out=None, lean=False):
         """The optimal-NPI Pareto sweep (TrainPredictPrescribeNPI.m:421-495,624-633) for all
         regions x all epsilon.  Per-region arrays are [n_regions, ...] row-major with the
         MATLAB column-major page inside ([T,L] days-major, [36] column-major).  `out`
@@ -379,6 +379,7 @@ class Engine:
         a.Ps_final = self._in(Ps_final, mem, n=nR * 36)
         a.Q = self._in(Q, mem, n=nR * 36)
         a.beta_ekf, a.gamma_ekf, a.W = float(beta_ekf), float(gamma_ekf), int(W)
+        a.lean = int(bool(lean))
         a.x0 = self._in(x0, mem, n=nR * 3)
         a.newcases_hist = self._in(newcases_hist, mem, n=nR * T_hist)
         a.weights = self._in(weights, mem, n=nR * T * L)

@@ -250,6 +250,14 @@ typedef struct {
   double *u_knee;              /* [n_regions][T-T_hist][L] schedule at the knee, or NULL */
   double *u_fore;              /* [T-T_hist][L][B] every smoothed schedule, or NULL */
   double *P_first;             /* [36][B] P_SMOOTH(:,:,1), or NULL */
+  int lean;                    /* 0: run the smoother over all T days, as the reference does.
+                                  1: every output of this call except P_first depends on the smoothed
+                                     states of the days to optimise only (on history days u is given, so
+                                     u_opt_smooth == u: GenericExtendedKalmanFilter.m:229 passes it through),
+                                     hence the smoother gains / backward recursion run for days >= T_hist
+                                     only and the forward tape keeps those days only.  Same J0, J1, front,
+                                     knee and schedules, bit for bit.  Requires a NaN-free history block of
+                                     u (else J1 = NaN) and P_first == NULL. */
 } epi_sweep_args;
 int epi_sweep(epi_ctx *ctx, const epi_sweep_args *a);
 

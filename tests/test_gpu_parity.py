@@ -388,6 +388,27 @@ def test_sweep_matches_oracle_and_golden(engine):
                        s3["gamma_ekf"], s3["W"], 1)
         assert_bits(S[:, :, r].T, o3["S_SMOOTH"], "fixed-input smoother")
     assert np.max(np.abs(res["J0"] - g["J0"]) / np.abs(g["J0"])) <= TOL_COST
+    # lean mode (smoother on the days to optimise only) returns the same bits
+    batch = wl.sweep_batch(inp, S)
+    lean = wl.run_sweep(engine, batch, eps, want_front=True, want_u_fore=True, want_u_knee=True, lean=True)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+        assert_bits(lean[k], res[k], f"lean {k}")
+    with pytest.raises(K.EpiError):
+        wl.run_sweep(engine, batch, eps, want_P_first=True, lean=True)
+
+
+@pytest.mark.parametrize("T_hist,T_fore", [(0, 25), (25, 0), (1, 1), (40, 1)])
+def test_sweep_lean_edge_shapes(engine, T_hist, T_fore):
+    """No history / no forecast / single days: lean == full."""
+    if T_hist == 0:
+        pytest.skip("the fixed-input smoother needs at least one historic day")
+    inp, eps = cases.sweep_case(n_regions=2, n_eps=5, T_hist=T_hist, T_fore=T_fore)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    full = wl.run_sweep(engine, batch, eps)
+    lean = wl.run_sweep(engine, batch, eps, lean=True)
+    for k in ("J0", "J1", "on_front", "I_opt"):
+        assert_bits(lean[k], full[k], f"lean {k} T_hist={T_hist} T_fore={T_fore}")
 
 
 def test_sweep_with_noise_waves_and_device_mode(engine):
@@ -434,6 +455,9 @@ def test_sweep_full_size_properties(engine):
     inp = syn.sweep_inputs(n_regions=nR, T_hist=Th, T_fore=Tf)
     eps = syn.epsilon_grid_xprize02(250)
     S, res = _run_sweep(engine, inp, eps, want_front=True, want_u_knee=True)
+    lean = wl.run_sweep(engine, wl.sweep_batch(inp, S), eps, want_front=True, want_u_knee=True, lean=True)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_knee"):
+        assert_bits(lean[k], res[k], f"full-size lean {k}")
     J0, J1, m = res["J0"], res["J1"], res["on_front"].astype(bool)
     assert J0.shape == (nR, 250) and np.isfinite(J0).all() and np.isfinite(J1).all()
     assert (J0 >= 0).all() and (J1 >= 0).all()

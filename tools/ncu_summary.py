@@ -88,27 +88,27 @@ def full(tag):
         for h, u, v in zip(hdr, units, vals):
             if any(h == k or (k in ("local_load", "local_store") and k in h) for k in KEYS) or "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
                 out.append(f"| {h} | {v} | {u} |")
-        # source page: top stall lines
-        srcp = ncu("-i", rep, "--page", "source", "--csv")
-        srows = list(csv.reader(io.StringIO(srcp)))
-        if len(srows) > 2:
-            h = srows[0]
-            try:
-                i_src = h.index("Source")
-                i_samp = next(i for i, c in enumerate(h) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)" or "Sampling (All" in c)
-                agg = []
-                for r in srows[1:]:
-                    try:
-                        agg.append((float(r[i_samp].replace(",", "") or 0), r[i_src]))
-                    except Exception:
-                        pass
-                agg.sort(reverse=True)
-                tot = sum(a for a, _ in agg) or 1
-                out.append("\n## top sampled lines\n")
-                for a, s in agg[:25]:
-                    out.append(f"- {100 * a / tot:.1f}%  `{s.strip()[:140]}`")
-            except Exception as e:  # pragma: no cover
-                out.append(f"\n(source page not parsed: {e})")
+        # source page (CUDA lines correlated with SASS): instructions and stall samples per line
+        srcp = ncu("-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass")
+        cur, agg = None, []
+        for r in csv.reader(io.StringIO(srcp)):
+            if len(r) == 2 and r[0] == "File Path":
+                cur = os.path.basename(r[1])
+                continue
+            if len(r) > 8 and r[0].isdigit() and r[2] == "-":
+                try:
+                    inst, samp = int(r[7]), int(r[6])
+                except ValueError:
+                    continue
+                if inst > 0 or samp > 0:
+                    agg.append((samp, inst, cur, int(r[0]), r[1].strip()[:110]))
+        if agg:
+            tot_i = sum(a_[1] for a_ in agg) or 1
+            tot_s = sum(a_[0] for a_ in agg) or 1
+            agg.sort(reverse=True)
+            out.append("\n## hottest source lines (share of warp-stall samples | share of executed instructions)\n")
+            for samp, inst, f, ln, txt in agg[:30]:
+                out.append(f"- {100 * samp / tot_s:4.1f}% | {100 * inst / tot_i:4.1f}%  `{f}:{ln}`  `{txt}`")
         path = os.path.join(PR, f"{tag}_{kname}.md")
         open(path, "w").write("\n".join(out) + "\n")
         print("wrote", path)
