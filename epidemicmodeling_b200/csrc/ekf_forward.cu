@@ -9,6 +9,8 @@
 // model scalars are read once; the per-day tape (S_MINUS, S_PLUS, P_MINUS, P_PLUS) is
 // written so that every store instruction of a warp is one contiguous 256-byte row
 // (tiled scratch: all offsets are instruction immediates).
+#include <type_traits>
+
 #include "ekf_common.cuh"
 
 namespace epi {
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
   constexpr int MM = M * M;
   constexpr int PF = (SYM && TILED) ? M * (M + 1) / 2 : MM;
   extern __shared__ double win[];  // MONITOR: [3][W][blockDim.x]
+  using TmpMat = Mat<M, false>;  // (a shared-memory backing, SMat, was tried: no register relief)
 
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
@@ -147,7 +150,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
       for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) Mx[i][j] = ((i == j) ? 1.0 : 0.0) - K[i] * C[j];
-      Mat<M, false> MP;
+      TmpMat MP;
 #pragma unroll
       for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
     state_eqs<MODEL>(mc, eps, sp, dotv, sn);
     Mat<M, false> A;
     state_jacobian<MODEL>(mc, eps, sp, a25, A);
-    Mat<M, false> AP;
+    TmpMat AP;
     mul_A_P<M, SYM>(A, Pp, AP);
     // :158 P(k+1|k) = A P A' + Q, :161 symmetrisation
     if (LEG) {
@@ -224,14 +227,14 @@ __global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__
       for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = 0; j < M; ++j)
-          Pm.at(i, j) = mul_X_At_ij<M, false>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
+          Pm.at(i, j) = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
     } else {
 #pragma unroll
       for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = i; j < M; ++j) {
-          const double pij = mul_X_At_ij<M, false>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
-          const double pji = mul_X_At_ij<M, false>(AP, A, j, i) + q_elem(in.Q, P.q_mode, M, k, j, i);
+          const double pij = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
+          const double pji = mul_X_At_ij<M>(AP, A, j, i) + q_elem(in.Q, P.q_mode, M, k, j, i);
           Pm.at(i, j) = (pij + pji) / 2.0;
         }
     }

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 #pragma unroll
       for (int i = 0; i < M; ++i)
 #pragma unroll
-        for (int j = 0; j < M; ++j) PAt.at(i, j) = mul_X_At_ij<M, true>(Pp, A, i, j);
+        for (int j = 0; j < M; ++j) PAt.at(i, j) = mul_X_At_ij<M>(Pp, A, i, j);
 #pragma unroll
       for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 #pragma unroll
     for (int i = 0; i < M; ++i)
 #pragma unroll
-      for (int j = 0; j < M; ++j) rhs.at(j, i) = mul_X_At_ij<M, false>(Pp, A, i, j);  // rhs = (P+ A')'
+      for (int j = 0; j < M; ++j) rhs.at(j, i) = mul_X_At_ij<M>(Pp, A, i, j);  // rhs = (P+ A')'
     lu_solve_inplace<M>(lu, rhs);
 #pragma unroll
     for (int i = 0; i < M; ++i)

@@ -93,6 +93,15 @@ struct Mat {
   EPI_DI double &at(int i, int j) { return v[idx(i, j)]; }
 };
 
+// the same interface backed by shared memory ([element][thread], conflict-free): used for the
+// 6x6 product temporaries of the forward pass to relieve register pressure
+template <int M, int STRIDE>
+struct SMat {
+  double *base;  // this thread's column of a [M*M][STRIDE] buffer
+  EPI_DI double operator()(int i, int j) const { return base[(i * M + j) * STRIDE]; }
+  EPI_DI double &at(int i, int j) { return base[(i * M + j) * STRIDE]; }
+};
+
 // trajectory-minor SoA addressing: X[t][f][b]
 struct Soa {
   size_t B;
@@ -329,8 +338,8 @@ EPI_DI double obs_model(int obs_type, const double *s, double v_bar, double *C) 
 // structured products (the summation order is part of the arithmetic contract)
 // ---------------------------------------------------------------------------
 // R = A * P, A with pattern a_nz
-template <int M, bool SYMP>
-EPI_DI void mul_A_P(const Mat<M, false> &A, const Mat<M, SYMP> &P, Mat<M, false> &R) {
+template <int M, bool SYMP, class RMat>
+EPI_DI void mul_A_P(const Mat<M, false> &A, const Mat<M, SYMP> &P, RMat &R) {
 #pragma unroll
   for (int i = 0; i < M; ++i)
 #pragma unroll
@@ -347,8 +356,8 @@ EPI_DI void mul_A_P(const Mat<M, false> &A, const Mat<M, SYMP> &P, Mat<M, false>
     }
 }
 // (X * A')(i,j) = sum_{l in nz(A row j)} X(i,l) A(j,l)
-template <int M, bool SYMX>
-EPI_DI double mul_X_At_ij(const Mat<M, SYMX> &X, const Mat<M, false> &A, int i, int j) {
+template <int M, class XMat>
+EPI_DI double mul_X_At_ij(const XMat &X, const Mat<M, false> &A, int i, int j) {
   double acc = 0.0;
   bool first = true;
 #pragma unroll

@@ -318,11 +318,18 @@ EPI_DI void bulk_load_row(void *sdst, const void *gsrc, unsigned bytes, unsigned
       : "memory");
 }
 
+// exact integer -> double without the multi-instruction I2F sequence: 2^52 + v has v in its
+// low mantissa bits, so (2^52 + v) - 2^52 == v exactly for 0 <= v < 2^32
+EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+EPI_DI double stage_value(const unsigned char *p) { return u32_to_double((unsigned)*p); }
+EPI_DI double stage_value(const double *p) { return *p; }
+
 template <int U_KIND, int SB, int TT>
 __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constant__ RolloutParams P) {
   using U = typename std::conditional<U_KIND == EPI_U_U8, unsigned char, double>::type;
   extern __shared__ __align__(128) unsigned char stage_raw[];  // [2][TT][L][SB] of U
   __shared__ unsigned long long bars[2];
+  __shared__ double wtile[TT * EPI_LMAX];  // this stage's day-wise weights (CTA within one group)
   const int tid = threadIdx.x;
   const long long blk0 = (long long)blockIdx.x * SB;
   const int b = (int)(blk0 + tid);
@@ -373,11 +380,18 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   const size_t ns = (size_t)P.noise.stride;
   const double *__restrict__ nz = (P.noise.p && active) ? P.noise.p + P.noise.off + b : nullptr;
 
+  // weights are per group: when the whole CTA lies in one group they are staged per time tile
+  const long long g_first = (P.b0 + blk0) / P.G, g_last = (P.b0 + blk0 + nb - 1) / P.G;
+  const bool w_tiled = want_cost && P.w && (g_first == g_last);
   for (int sidx = 0; sidx < n_stages; ++sidx) {
-    mbar_wait(&bars[sidx & 1], (unsigned)((sidx >> 1) & 1));
-    const U *__restrict__ su = stage_u + (size_t)(sidx & 1) * stage_elems + tid;
     const int t0 = sidx * TT;
     const int nt = (K - t0 < TT) ? (K - t0) : TT;
+    if (w_tiled) {
+      for (int q = tid; q < nt * L; q += SB) wtile[q] = __ldg(P.w + ((size_t)g_first * K + t0) * L + q);
+      __syncthreads();
+    }
+    mbar_wait(&bars[sidx & 1], (unsigned)((sidx >> 1) & 1));
+    const U *__restrict__ su = stage_u + (size_t)(sidx & 1) * stage_elems + tid;
     if (active) {
       // the input term and the day's weighted cost do not depend on the state: evaluate them
       // for DQ days at once (independent FMA chains = instruction-level parallelism), then run
@@ -390,15 +404,16 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
           dotq[q] = 0.0; cq[q] = 0.0;
           const int tt = tq + q;
           if (tt < nt) {
-            const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + (t0 + tt)) * L : nullptr;
+            const double *wd = w_tiled ? wtile + tt * L
+                               : ((want_cost && P.w) ? P.w + ((size_t)g * K + (t0 + tt)) * L : nullptr);
 #pragma unroll
             for (int j = 0; j < EPI_LMAX; ++j) {
               if (j < L) {
-                const double uj = (double)su[(size_t)(tt * L + j) * SB];
+                const double uj = stage_value(su + (size_t)(tt * L + j) * SB);
                 const double d = um[j] - uj;
                 dotq[q] = (j == 0) ? ga[j] * d : fma(ga[j], d, dotq[q]);
                 if (wd) {
-                  const double wu = __ldg(wd + j) * uj;
+                  const double wu = wd[j] * uj;
                   cq[q] = (j == 0) ? wu : (cq[q] + wu);
                 }
               }

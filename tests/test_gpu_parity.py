@@ -115,7 +115,8 @@ def test_sialpha_controlled_signature(engine, noisy):
         assert_bits(got[0], g["s"]); assert_bits(got[1], g["i"]); assert_bits(got[2], g["alpha"])
 
 
-@pytest.mark.parametrize("u_kind,nS", [("f64", 257), ("u8", 257), ("f64", 1024), ("u8", 1024), ("u8", 1000)])
+@pytest.mark.parametrize("u_kind,nS", [("f64", 257), ("u8", 257), ("f64", 1024), ("u8", 1024), ("u8", 1000),
+                                          ("u8", 1040), ("f64", 1040)])
 def test_rollout_cost_batch(engine, u_kind, nS):
     """BASELINE config 5 shape, small: regions x random schedules x 45 days with NPICost fused.
     nS = 1024 takes the TMA-staged kernel (aligned rows), 257 / 1000(u8: rows not 16-byte

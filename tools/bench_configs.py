@@ -43,6 +43,7 @@ def timed(fn, reps=5, warm=2):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--only", type=int, default=0, help="run a single config (2, 3 or 5)")
     a = ap.parse_args()
     eng = Engine(0)
     eng.use_torch_stream()
@@ -50,99 +51,105 @@ def main():
     out = []
     dev = "cuda:0"
 
+    nR = 236
+    holder = {}
+    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
     # ---- config 2: SEIRP ensemble, 1M x 365 days
-    B, Kn = int(1_000_000 * a.scale), 365
-    rates, ic = syn.seirp_ensemble(B)
-    rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
-    for mode, name in ((K.SEIRP_OUT_FULL, "full"), (K.SEIRP_OUT_FINAL, "final")):
-        ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, out_mode=mode))
-        steps = B * (Kn - 1)
-        rec = {"config": 2, "kernel": f"seirp[{name}]", "B": B, "K": Kn, "ms": ms, "steps_per_s": steps / ms * 1e3,
-               "hbm_gbs": (40.0 * B * Kn / ms * 1e3 / 1e9) if mode == K.SEIRP_OUT_FULL else 0.0,
-               "fp64_tflops": 37.0 * steps / ms * 1e3 / 1e12}
-        rec["hbm_frac"] = rec["hbm_gbs"] / HBM
-        rec["fp64_frac"] = rec["fp64_tflops"] / fp64
-        out.append(rec)
-    del rd, icd
-    sat = dict(beta_0=0.1, beta_s=0.01, mu_0=0.02, mu_s=0.2, sigma=1.0, i_0=0.1)
-    rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
-    ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, saturated=sat, out_mode=K.SEIRP_OUT_FINAL))
-    out.append({"config": 2, "kernel": "seirp_saturated[final]", "B": B, "K": Kn, "ms": ms,
-                "steps_per_s": B * (Kn - 1) / ms * 1e3})
-    del rd, icd
-    torch.cuda.empty_cache()
+    if a.only in (0, 2):
+        B, Kn = int(1_000_000 * a.scale), 365
+        rates, ic = syn.seirp_ensemble(B)
+        rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
+        for mode, name in ((K.SEIRP_OUT_FULL, "full"), (K.SEIRP_OUT_FINAL, "final")):
+            ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, out_mode=mode))
+            steps = B * (Kn - 1)
+            rec = {"config": 2, "kernel": f"seirp[{name}]", "B": B, "K": Kn, "ms": ms, "steps_per_s": steps / ms * 1e3,
+                   "hbm_gbs": (40.0 * B * Kn / ms * 1e3 / 1e9) if mode == K.SEIRP_OUT_FULL else 0.0,
+                   "fp64_tflops": 37.0 * steps / ms * 1e3 / 1e12}
+            rec["hbm_frac"] = rec["hbm_gbs"] / HBM
+            rec["fp64_frac"] = rec["fp64_tflops"] / fp64
+            out.append(rec)
+        del rd, icd
+        sat = dict(beta_0=0.1, beta_s=0.01, mu_0=0.02, mu_s=0.2, sigma=1.0, i_0=0.1)
+        rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
+        ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, saturated=sat, out_mode=K.SEIRP_OUT_FINAL))
+        out.append({"config": 2, "kernel": "seirp_saturated[final]", "B": B, "K": Kn, "ms": ms,
+                    "steps_per_s": B * (Kn - 1) / ms * 1e3})
+        del rd, icd
+        torch.cuda.empty_cache()
 
     # ---- config 3: SI-alpha EKF + smoother, 236 regions x replicates x 400 days
-    nR, nRep, T = 236, int(10_000 * a.scale), 400
-    inp = syn.sweep_inputs(n_regions=nR, T_hist=T, T_fore=0)
-    b = wl.fixed_input_batch(inp)
-    Bt = nR * nRep
-    clean = torch.from_numpy(np.stack([r["x"] for r in inp])).to(dev)            # [nR,T]
-    g = torch.Generator(device=dev).manual_seed(3)
-    x = torch.empty((T, Bt), dtype=torch.float64, device=dev)
-    for r in range(nR):
-        x[:, r * nRep:(r + 1) * nRep] = torch.clamp_min(
-            clean[r][:, None] * (1.0 + 0.05 * torch.randn((T, nRep), dtype=torch.float64, device=dev, generator=g)), 0.0)
-    t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
-    args = (params_to_device(b["prm"], dev), t(b["u"]), x, t(b["R"]), t(b["Q"]), t(b["s_init"]), t(b["Ps_init"]),
-            t(b["s_final"]), t(b["Ps_final"]))
-    kw = dict(B=Bt, T=T, L=b["L"], G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=1.0,
-              gamma=b["gamma"], W=b["W"], outputs=("S_SMOOTH",))
-    holder = {}
+    if a.only in (0, 3):
+        nR, nRep, T = 236, int(10_000 * a.scale), 400
+        inp = syn.sweep_inputs(n_regions=nR, T_hist=T, T_fore=0)
+        b = wl.fixed_input_batch(inp)
+        Bt = nR * nRep
+        clean = torch.from_numpy(np.stack([r["x"] for r in inp])).to(dev)            # [nR,T]
+        g = torch.Generator(device=dev).manual_seed(3)
+        x = torch.empty((T, Bt), dtype=torch.float64, device=dev)
+        for r in range(nR):
+            x[:, r * nRep:(r + 1) * nRep] = torch.clamp_min(
+                clean[r][:, None] * (1.0 + 0.05 * torch.randn((T, nRep), dtype=torch.float64, device=dev, generator=g)), 0.0)
+        t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+        args = (params_to_device(b["prm"], dev), t(b["u"]), x, t(b["R"]), t(b["Q"]), t(b["s_init"]), t(b["Ps_init"]),
+                t(b["s_final"]), t(b["Ps_final"]))
+        kw = dict(B=Bt, T=T, L=b["L"], G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=1.0,
+                  gamma=b["gamma"], W=b["W"], outputs=("S_SMOOTH",))
+        holder = {}
 
-    eng.set_scratch_limit(48 << 30)   # keep the waves' scratch in the pool instead of fighting torch's allocator
+        eng.set_scratch_limit(48 << 30)   # keep the waves' scratch in the pool instead of fighting torch's allocator
 
-    def run3():
+        def run3():
+            holder.clear()
+            holder["o"] = eng.ekf_eks(K.MODEL_SIALPHA, *args, **kw)
+        ms = timed(run3, reps=3, warm=1)
+        eng.set_scratch_limit(0)
+        kt = eng.last_kernel_times()
+        units = Bt * T
+        out.append({"config": 3, "kernel": "ekf_eks<3> lean (S_SMOOTH out)", "B": Bt, "T": T, "ms": ms,
+                    "trajectory_days_per_s": units / ms * 1e3, "kernel_ms": kt, "kernel_ms_sum": sum(kt.values()),
+                    "hbm_gbs_algorithmic(616B)": 616.0 * units / ms * 1e3 / 1e9,
+                    "hbm_frac": 616.0 * units / ms * 1e3 / 1e9 / HBM,
+                    "fp64_frac(818flop)": 818.0 * units / ms * 1e3 / 1e12 / fp64})
         holder.clear()
-        holder["o"] = eng.ekf_eks(K.MODEL_SIALPHA, *args, **kw)
-    ms = timed(run3, reps=3, warm=1)
-    eng.set_scratch_limit(0)
-    kt = eng.last_kernel_times()
-    units = Bt * T
-    out.append({"config": 3, "kernel": "ekf_eks<3> lean (S_SMOOTH out)", "B": Bt, "T": T, "ms": ms,
-                "trajectory_days_per_s": units / ms * 1e3, "kernel_ms": kt, "kernel_ms_sum": sum(kt.values()),
-                "hbm_gbs_algorithmic(616B)": 616.0 * units / ms * 1e3 / 1e9,
-                "hbm_frac": 616.0 * units / ms * 1e3 / 1e9 / HBM,
-                "fp64_frac(818flop)": 818.0 * units / ms * 1e3 / 1e12 / fp64})
-    holder.clear()
-    del x, args
-    torch.cuda.empty_cache()
+        del x, args
+        torch.cuda.empty_cache()
 
     # ---- config 5: random-NPI Monte-Carlo scoring, 236 regions x 100k schedules x 120 days (uint8 NPIs)
-    nS, Kn, L = int(100_000 * a.scale), 120, 12
-    reg = syn.load_regions(nR)
-    Bm = nR * nS
-    umax = torch.tensor(reg["npi_max"], dtype=torch.float64, device=dev)
-    u8 = torch.empty((Kn, L, Bm), dtype=torch.uint8, device=dev)
-    g = torch.Generator(device=dev).manual_seed(5)
-    for j in range(L):  # TrainPredictPrescribeNPI.m:500-510: first half constant in time, second half per day
-        hi = int(reg["npi_max"][j]) + 1
-        per_day = torch.randint(0, hi, (Kn, Bm), dtype=torch.uint8, device=dev, generator=g)
-        const = torch.randint(0, hi, (1, Bm), dtype=torch.uint8, device=dev, generator=g)
-        first_half = (torch.arange(Bm, device=dev) % nS) < (nS // 2)
-        u8[:, j, :] = torch.where(first_half[None, :], const.expand(Kn, Bm), per_day)
-        del per_day, const
-    prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
-                            alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
-    x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)]))
-    w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)]))
-    j0p, j1p = torch.zeros(nR, dtype=torch.float64, device=dev), torch.zeros(nR, dtype=torch.float64, device=dev)
-    prmd = params_to_device(prm, dev)
+    if a.only in (0, 5):
+        nS, Kn, L = int(100_000 * a.scale), 120, 12
+        reg = syn.load_regions(nR)
+        Bm = nR * nS
+        umax = torch.tensor(reg["npi_max"], dtype=torch.float64, device=dev)
+        u8 = torch.empty((Kn, L, Bm), dtype=torch.uint8, device=dev)
+        g = torch.Generator(device=dev).manual_seed(5)
+        for j in range(L):  # TrainPredictPrescribeNPI.m:500-510: first half constant in time, second half per day
+            hi = int(reg["npi_max"][j]) + 1
+            per_day = torch.randint(0, hi, (Kn, Bm), dtype=torch.uint8, device=dev, generator=g)
+            const = torch.randint(0, hi, (1, Bm), dtype=torch.uint8, device=dev, generator=g)
+            first_half = (torch.arange(Bm, device=dev) % nS) < (nS // 2)
+            u8[:, j, :] = torch.where(first_half[None, :], const.expand(Kn, Bm), per_day)
+            del per_day, const
+        prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                                alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
+        x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)]))
+        w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)]))
+        j0p, j1p = torch.zeros(nR, dtype=torch.float64, device=dev), torch.zeros(nR, dtype=torch.float64, device=dev)
+        prmd = params_to_device(prm, dev)
 
-    def run5():
-        holder["o"] = eng.rollout_cost(prmd, x0, u8, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
-                                       T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w)
-    ms = timed(run5, reps=3, warm=1)
-    units = Bm * Kn
-    out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
-                "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
-                "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
+        def run5():
+            holder["o"] = eng.rollout_cost(prmd, x0, u8, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
+                                           T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w)
+        ms = timed(run5, reps=3, warm=1)
+        units = Bm * Kn
+        out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
+                    "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
+                    "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
 
-    J0, J1 = holder["o"]["J0"].view(nR, nS), holder["o"]["J1"].view(nR, nS)
-    ms = timed(lambda: holder.__setitem__("p", eng.pareto(J0, J1)), reps=3, warm=1)
-    mask, iopt = holder["p"]
-    out.append({"config": 5, "kernel": "pareto[sorted]", "n_sets": nR, "n": nS, "ms": ms,
-                "points_per_s": nR * nS / ms * 1e3, "front_sizes_mean": float(mask.sum(dim=1).double().mean().item())})
+        J0, J1 = holder["o"]["J0"].view(nR, nS), holder["o"]["J1"].view(nR, nS)
+        ms = timed(lambda: holder.__setitem__("p", eng.pareto(J0, J1)), reps=3, warm=1)
+        mask, iopt = holder["p"]
+        out.append({"config": 5, "kernel": "pareto[sorted]", "n_sets": nR, "n": nS, "ms": ms,
+                    "points_per_s": nR * nS / ms * 1e3, "front_sizes_mean": float(mask.sum(dim=1).double().mean().item())})
 
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "w") as f:
