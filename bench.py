@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--t-fore", type=int, default=120)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-lean", action="store_true", help="skip the extra lean-mode leg (profiling runs)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
@@ -278,21 +279,20 @@ def main():
 
     # extra (not the headline): the lean sweep mode -- identical outputs, smoother only on the days
     # whose schedule is optimised (include/epi_b200.h: epi_sweep_args.lean)
-    out_lean = {k: torch.empty_like(v) for k, v in out.items()}
-    for _ in range(3):
-        wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
-    fence()
-    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0.record()
-    for _ in range(a.steps):
-        wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
-    l1.record()
-    fence()
-    ms_lean = l0.elapsed_time(l1) / a.steps
-    lean_same = all(bool(torch.equal(out_lean[k], out[k])) for k in out)
-    # restore the per-kernel timings of the full mode for the roofline below
-    step()
-    torch.cuda.synchronize()
+    ms_lean, lean_same = None, None
+    if not a.no_lean:
+        out_lean = {k: torch.empty_like(v) for k, v in out.items()}
+        for _ in range(3):
+            wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
+        fence()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(a.steps):
+            wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
+        l1.record()
+        fence()
+        ms_lean = l0.elapsed_time(l1) / a.steps
+        lean_same = all(bool(torch.equal(out_lean[k], out[k])) for k in out)
 
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -389,7 +389,23 @@ def main():
         t0 = time.perf_counter()
         j0, j1, _, _ = orc.sweep_batch(regs, eps, n_threads=cores)
         dt = time.perf_counter() - t0
+        # B3: the interpreter regime the reference actually runs in (MATLAB/Octave are absent):
+        # the NumPy twin of the same .m files, one core, a handful of trajectories
+        from oracle import numpy_twin as tw
+        rin = inp[0]
+        s6 = rin["setup6"]
+        u6 = np.concatenate([rin["u_hist"], np.full((12, a.t_fore), np.nan)], axis=1)
+        tw0 = time.perf_counter()
+        n_tw = 0
+        for e in eps[:: max(1, nE // 3)][:3]:
+            tw.ekf_eks("optctrl", False, u6, rin["x"], dict(s6["params"], epsilon=float(e)), s6["s_init"], s6["Ps_init"],
+                       s6["s_final"], s6["Ps_final"], 0.0, s6["Q_w"], rin["R_v"], s6["beta_ekf"], s6["gamma_ekf"], s6["W"])
+            n_tw += 1
+        tw_dt = time.perf_counter() - tw0
         cpu = {"value": n * nE * T / dt, "unit": "trajectory-days/s", "cores": cores, "kind": "port",
+               "interpreted_proxy": {"value": n_tw * T / tw_dt, "unit": "trajectory-days/s", "cores": 1,
+                                     "what": "NumPy twin of the same .m files (interpreter regime; EKF/EKS only)",
+                                     "sample": f"{n_tw} trajectories x {T} days, {tw_dt:.2f} s"},
                "sample": f"{n} of {nR} regions x {nE} eps x {T} days, {dt:.1f} s (C oracle, OpenMP)",
                "parity_with_gpu_bit_exact": bool(np.array_equal(j0, out["J0"].cpu().numpy()[:n]) and
                                                  np.array_equal(j1, out["J1"].cpu().numpy()[:n]))}
@@ -405,7 +421,8 @@ def main():
                            "mode_e2e": "EPI_MEM_HOST (pinned host buffers, blocking call)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu,
-                "lean_mode": {"value": units_rank * world / (ms_lean * 1e-3), "unit": "trajectory-days/s",
+                "lean_mode": None if ms_lean is None else {
+                              "value": units_rank * world / (ms_lean * 1e-3), "unit": "trajectory-days/s",
                               "ms_per_step": ms_lean, "outputs_bit_identical_to_full": lean_same,
                               "note": "not the headline: smoother gains/backward only on the days to optimise "
                                       "(epi_sweep_args.lean); same J0/J1/front/knee bits"}}

@@ -96,6 +96,7 @@ SYMBOLS = {
     "epi_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "epi_sync": (C.c_int, [C.c_void_p]),
     "epi_set_scratch_limit": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "epi_release_cache": (C.c_int, [C.c_void_p]),
     "epi_launch_count": (C.c_longlong, [C.c_void_p]),
     "epi_last_kernel_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.c_int]),
     "epi_fp64_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),

@@ -326,6 +326,10 @@ extern "C" int epi_set_scratch_limit(epi_ctx *c, size_t bytes) {
   return EPI_OK;
 }
 
+extern "C" int epi_release_cache(epi_ctx *c) {
+  return guarded(c, [&] { trim_cache(c); });
+}
+
 extern "C" long long epi_launch_count(const epi_ctx *c) { return c ? c->launches : 0; }
 
 extern "C" int epi_last_kernel_times(epi_ctx *c, float *ms, const char **names, int max) {

@@ -111,6 +111,10 @@ class Engine:
     def set_scratch_limit(self, nbytes):
         self._ck(self._lib.epi_set_scratch_limit(self._h, int(nbytes)))
 
+    def release_cache(self):
+        """Return the context's cached device blocks to the driver."""
+        self._ck(self._lib.epi_release_cache(self._h))
+
     @property
     def launch_count(self):
         return int(self._lib.epi_launch_count(self._h))

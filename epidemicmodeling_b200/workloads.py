@@ -102,6 +102,42 @@ def run_sweep(engine, batch, eps, **kw):
                         W=batch["W"], **kw)
 
 
+def forecast_quality(engine, inputs, num_forecast_days, max_look_ahead_days, truth=None):
+    """The masked-horizon loop of Tools/ForecastQualityAssessment.m:383-394 as ONE batch:
+    for start = 1..num_forecast_days the last `start` observations are set to NaN and the
+    3-state EKF/EKS is re-run (SIAlphaModelEKF with the region's full NPI history).
+    One group per region, `num_forecast_days` trajectories per group, x per trajectory.
+
+    inputs: per-region dicts with u (L x T, key "u_fixed"), x (T), R_v (T), setup3 (synthetic.py).
+    truth:  [nR, T] ground-truth new cases (fractions of N); default = the unmasked observations.
+    Returns S_PLUS, S_SMOOTH [T,3,nR*nf] and EstError_PLUS / EstError_SMOOTH [nR, nf, max_look_ahead]
+    (percent errors; NaN where the reference leaves its preallocated zeros untouched is kept as 0)."""
+    b = fixed_input_batch(inputs)
+    nR, T, nf = b["n_regions"], b["T"], int(num_forecast_days)
+    x = np.repeat(b["x"].T[:, :, None], nf, axis=2)                 # [T, nR, nf]
+    for start in range(1, nf + 1):
+        x[T - start:, :, start - 1] = np.nan                        # observations_PARTIAL(LL-start+1:LL) = nan
+    x = np.ascontiguousarray(x.reshape(T, nR * nf))
+    out = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"],
+                         b["s_final"], b["Ps_final"], B=nR * nf, T=T, L=b["L"], G=nf, x_per_traj=True,
+                         r_mode=K.R_PERDAY, fixed_R=False, q_mode=K.Q_CONST, beta=b["beta"], gamma=b["gamma"],
+                         W=b["W"], order=1, outputs=("S_PLUS", "S_SMOOTH"))
+    truth = b["x"] if truth is None else np.asarray(truth, dtype=np.float64)
+    err = {}
+    for key in ("S_PLUS", "S_SMOOTH"):
+        S = np.asarray(out[key]).reshape(T, 3, nR, nf)
+        est = (S[:, 0] * S[:, 1]) * S[:, 2]                         # s.*i.*alpha  [T, nR, nf]
+        e = 100.0 * np.abs(truth.T[:, :, None] - est) / truth.T[:, :, None]
+        E = np.zeros((nR, nf, max_look_ahead_days))
+        for start in range(1, nf + 1):                               # :392-394
+            last = min(T, T - start + max_look_ahead_days)
+            n = last - T + start
+            E[:, start - 1, :n] = e[T - start:last, :, start - 1].T
+        err[key] = E
+    return dict(S_PLUS=out["S_PLUS"], S_SMOOTH=out["S_SMOOTH"], EstError_PLUS=err["S_PLUS"],
+                EstError_SMOOTH=err["S_SMOOTH"])
+
+
 def shard_regions(n_regions, world_size, rank):
     """Contiguous blocks of ceil(n/G) regions per rank."""
     per = (n_regions + world_size - 1) // world_size

@@ -95,6 +95,9 @@ int epi_sync(epi_ctx *ctx);
 /* cap on library-owned scratch (tape) bytes; larger batches are processed in
  * waves of trajectories.  0 = default (60 % of free device memory). */
 int epi_set_scratch_limit(epi_ctx *ctx, size_t bytes);
+/* The context caches the device blocks it allocated (staging, scratch) for reuse by later
+ * calls; this hands them all back to the driver (synchronises the stream first). */
+int epi_release_cache(epi_ctx *ctx);
 /* kernel launches issued by this context since creation (bench `gpu_launches`) */
 long long epi_launch_count(const epi_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) of the kernels of the

@@ -481,3 +481,27 @@ def test_sweep_full_size_properties(engine):
                             rin["weights"])
         j0, j1, _, _, _ = o.sweep_region(reg, eps[e:e + 1])
         assert J0[r, e] == j0[0] and J1[r, e] == j1[0], (r, e)
+
+
+# ------------------------------------------------------------------------------ next row
+def test_forecast_quality_loop(engine):
+    """Tools/ForecastQualityAssessment.m:383-394: masked-horizon re-runs as one batch vs the oracle loop."""
+    inp = syn.sweep_inputs(n_regions=2, T_hist=70, T_fore=0)
+    nf, look = 9, 5
+    res = wl.forecast_quality(engine, inp, nf, look)
+    T = inp[0]["T"]
+    o = orc()
+    for r, rin in enumerate(inp):
+        s3 = rin["setup3"]
+        for start in (1, 4, nf):
+            xp = rin["x"].copy()
+            xp[T - start:] = np.nan
+            want = o.ekf_eks(o.SIALPHA, rin["u_fixed"], xp, s3["params"], s3["s_init"], s3["Ps_init"], s3["s_final"],
+                             s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], rin["R_v"], 1.0, s3["gamma_ekf"], s3["W"], 1)
+            b = r * nf + start - 1
+            assert_bits(res["S_PLUS"][:, :, b].T, want["S_PLUS"], "forecast-quality S_PLUS")
+            assert_bits(res["S_SMOOTH"][:, :, b].T, want["S_SMOOTH"], "forecast-quality S_SMOOTH")
+            est = (want["S_SMOOTH"][0] * want["S_SMOOTH"][1]) * want["S_SMOOTH"][2]
+            e = 100.0 * np.abs(rin["x"] - est) / rin["x"]
+            last = min(T, T - start + look)
+            assert np.array_equal(res["EstError_SMOOTH"][r, start - 1, :last - T + start], e[T - start:last])

@@ -60,9 +60,11 @@ def main():
         rates, ic = syn.seirp_ensemble(B)
         rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
         for mode, name in ((K.SEIRP_OUT_FULL, "full"), (K.SEIRP_OUT_FINAL, "final")):
-            ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, out_mode=mode))
+            ms_call = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, out_mode=mode))
+            ms = sum(eng.last_kernel_times().values())   # CUDA events around the kernel, on its stream
             steps = B * (Kn - 1)
-            rec = {"config": 2, "kernel": f"seirp[{name}]", "B": B, "K": Kn, "ms": ms, "steps_per_s": steps / ms * 1e3,
+            rec = {"config": 2, "kernel": f"seirp[{name}]", "B": B, "K": Kn, "ms": ms,
+                   "ms_call_incl_output_alloc": ms_call, "steps_per_s": steps / ms * 1e3,
                    "hbm_gbs": (40.0 * B * Kn / ms * 1e3 / 1e9) if mode == K.SEIRP_OUT_FULL else 0.0,
                    "fp64_tflops": 37.0 * steps / ms * 1e3 / 1e12}
             rec["hbm_frac"] = rec["hbm_gbs"] / HBM
@@ -71,11 +73,13 @@ def main():
         del rd, icd
         sat = dict(beta_0=0.1, beta_s=0.01, mu_0=0.02, mu_s=0.2, sigma=1.0, i_0=0.1)
         rd, icd = torch.from_numpy(rates).to(dev), torch.from_numpy(ic).to(dev)
-        ms = timed(lambda: eng.seirp(rd, icd, Kn, 1.0, saturated=sat, out_mode=K.SEIRP_OUT_FINAL))
+        timed(lambda: eng.seirp(rd, icd, Kn, 1.0, saturated=sat, out_mode=K.SEIRP_OUT_FINAL))
+        ms = sum(eng.last_kernel_times().values())
         out.append({"config": 2, "kernel": "seirp_saturated[final]", "B": B, "K": Kn, "ms": ms,
                     "steps_per_s": B * (Kn - 1) / ms * 1e3})
         del rd, icd
         torch.cuda.empty_cache()
+        eng.release_cache()
 
     # ---- config 3: SI-alpha EKF + smoother, 236 regions x replicates x 400 days
     if a.only in (0, 3):
@@ -113,6 +117,7 @@ def main():
         holder.clear()
         del x, args
         torch.cuda.empty_cache()
+        eng.release_cache()
 
     # ---- config 5: random-NPI Monte-Carlo scoring, 236 regions x 100k schedules x 120 days (uint8 NPIs)
     if a.only in (0, 5):
@@ -139,7 +144,8 @@ def main():
         def run5():
             holder["o"] = eng.rollout_cost(prmd, x0, u8, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
                                            T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w)
-        ms = timed(run5, reps=3, warm=1)
+        ms_call = timed(run5, reps=3, warm=1)
+        ms = sum(eng.last_kernel_times().values())
         units = Bm * Kn
         out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
                     "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
