@@ -368,8 +368,16 @@ def main():
                    "hbm_gbs": ab * units_rank / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
                    "fp64_tflops": fl * units_rank / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
     achieved = kern[dom]["hbm_gbs"]
+    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        if (a.regions, a.eps, a.t_hist, a.t_fore) == (236, 250, 441, 120):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom]["traffic"]
+    except Exception:
+        traffic = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": "profiles/r01_traffic.json (ncu --set full, per launch)" if traffic else None,
+                "algorithmic_bytes_per_launch": KERNEL_ALGO[dom][0] * units_rank, "peak_source": peak_src,
                 "algorithmic_bytes_per_trajectory_day": KERNEL_ALGO[dom][0],
                 "fp64": {"achieved_tflops": kern[dom]["fp64_tflops"], "peak_tflops_measured": fp64_tflops,
                          "frac": kern[dom]["fp64_tflops"] / fp64_tflops if fp64_tflops else None,
