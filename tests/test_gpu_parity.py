@@ -505,3 +505,86 @@ def test_forecast_quality_loop(engine):
             e = 100.0 * np.abs(rin["x"] - est) / rin["x"]
             last = min(T, T - start + look)
             assert np.array_equal(res["EstError_SMOOTH"][r, start - 1, :last - T + start], e[T - start:last])
+
+
+# ------------------------------------------------------------------------------ per-trajectory inputs, Q/R modes
+@pytest.mark.parametrize("q_mode", ["const", "perday_scalar", "perday_full"])
+def test_ekf3_everything_per_trajectory(engine, q_mode):
+    """u, x, R, initial/final conditions per trajectory and the three Q shapes of
+    GenericExtendedKalmanFilter.m:64-77 (square => constant, length-T vector, m x m x T)."""
+    rng = np.random.default_rng(101)
+    B, T, L, m = 37, 55, 12, 3
+    reg = syn.load_regions(4)
+    base = [cases.ekf3_case(r, T_hist=T - 10, T_fore=10) for r in range(4)]
+    u = np.empty((T, L, B)); x = np.empty((T, B)); R = np.empty((T, B))
+    s_init = np.empty((m, B)); Ps_init = np.empty((m * m, B)); s_final = np.empty((m, B)); Ps_final = np.empty((m * m, B))
+    per = []
+    for b in range(B):
+        c = base[b % 4]
+        ub = c["u"].copy(); ub[:, rng.integers(0, T, 5)] = rng.integers(0, 3, (L, 5))
+        xb = c["x"] * (1 + 0.02 * rng.standard_normal(T))
+        Rb = c["R_v"] * (1 + 0.5 * rng.random(T))
+        si = c["s_init"] * np.array([1.0, 1 + 0.1 * rng.random(), 1 + 0.05 * rng.random()])
+        Pi = np.asarray(c["Ps_init"]) * (1 + rng.random())
+        sf = np.array([np.nan, np.nan, 0.1 + 0.05 * rng.random()]) if b % 3 == 0 else np.full(3, np.nan)
+        Pf = np.full((3, 3), np.nan)
+        if b % 3 == 0:
+            Pf[2, 2] = 1e-4
+        u[:, :, b], x[:, b], R[:, b] = ub.T, xb, Rb
+        s_init[:, b], Ps_init[:, b], s_final[:, b], Ps_final[:, b] = si, Pi.T.ravel(), sf, Pf.T.ravel()
+        per.append((c, ub, xb, Rb, si, Pi, sf, Pf))
+    prm = pack_params([base[g]["params"] for g in range(4)] * 10, L)[:B]  # one group per trajectory (G = 1)
+    prm = pack_params([base[b % 4]["params"] for b in range(B)], L)
+    Q0 = np.asarray(base[0]["Q_w"])
+    if q_mode == "const":
+        Qarg, qm, Qm = np.stack([Q0.T.ravel()] * B), K.Q_CONST, Q0
+    elif q_mode == "perday_scalar":
+        qv = 1e-10 * (1 + rng.random(T))
+        Qarg, qm, Qm = np.stack([qv] * B), K.Q_PERDAY_SCALAR, qv
+    else:
+        Q3 = np.stack([Q0 * (1 + 0.3 * rng.random()) for _ in range(T)], axis=2)   # m x m x T
+        Qarg, qm, Qm = np.stack([np.transpose(Q3, (2, 1, 0)).ravel()] * B), K.Q_PERDAY_FULL, Q3
+    out = engine.ekf_eks(K.MODEL_SIALPHA, prm, u, x, R, Qarg, s_init, Ps_init, s_final, Ps_final, B=B, T=T, L=L,
+                         G=1, u_per_traj=True, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, r_per_traj=True,
+                         q_mode=qm, init_per_traj=True, beta=1.0, gamma=0.995, W=21)
+    o = orc()
+    for b in (0, 1, 2, 3, 17, B - 1):
+        c, ub, xb, Rb, si, Pi, sf, Pf = per[b]
+        want = o.ekf_eks(o.SIALPHA, ub, xb, c["params"], si, Pi, sf, Pf, c["w_bar"], 0.0, Qm, Rb, 1.0, 0.995, 21, 1)
+        for k in ("S_MINUS", "S_PLUS", "S_SMOOTH", "u_opt", "u_opt_smooth"):
+            assert_bits(out[k][:, :, b].T, want[k], f"{q_mode} b={b} {k}")
+        for k in ("P_MINUS", "P_PLUS", "P_SMOOTH"):
+            assert_bits(out[k][:, :, b].reshape(T, 3, 3).transpose(2, 1, 0), want[k], f"{q_mode} b={b} {k}")
+        assert_bits(out["rho"][:, b], want["rho"][:, 0], "rho")
+
+
+def test_ekf_scalar_R_per_trajectory_adaptive_and_legacy_batch(engine):
+    """Constant R given per trajectory with adaptation (beta_ekf = 0.9), generic 3-state and the legacy
+    6-state monolith as a batch of different epsilon."""
+    c = cases.ekf3_case(1, variant="adaptive")
+    B, T, L = 5, c["u"].shape[1], 12
+    Rs = float(np.asarray(c["R_v"]).ravel()[0]) * np.array([0.5, 1.0, 2.0, 4.0, 8.0])
+    cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+    out = engine.ekf_eks(K.MODEL_SIALPHA, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], Rs, cm(c["Q_w"]),
+                         c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]), B=B, T=T, L=L, G=B,
+                         r_mode=K.R_CONST, fixed_R=True, r_per_traj=True, beta=0.9, gamma=c["gamma"], W=21,
+                         outputs=("S_SMOOTH", "rho", "K_GAIN"))
+    o = orc()
+    for b in range(B):
+        a = list(ekf_args(c)); a[10] = np.array([[Rs[b]]])
+        want = o.ekf_eks(o.SIALPHA, *a)
+        assert_bits(out["S_SMOOTH"][:, :, b].T, want["S_SMOOTH"], f"adaptive R b={b}")
+        assert_bits(out["rho"][:, b], want["rho"][:, 0], f"adaptive rho b={b}")
+    lc = cases.legacy_case(0)
+    eps = np.array([0.05, 0.2, 0.6])
+    T = lc["u"].shape[1]
+    out = engine.ekf_eks(K.MODEL_LEGACY_TOOLS, pack_params([lc["params"]], L), lc["u"].T.copy(), lc["x"],
+                         np.asarray(lc["R_v"]).ravel(), cm(lc["Q_w"]), lc["s_init"], cm(lc["Ps_init"]), lc["s_final"],
+                         cm(lc["Ps_final"]), B=3, T=T, L=L, G=3, epsilon=eps, r_mode=K.R_CONST, beta=lc["beta"],
+                         gamma=lc["gamma"], W=21, outputs=("u_opt", "S_SMOOTH", "P_SMOOTH", "rho"))
+    for e, ev in enumerate(eps):
+        a = list(ekf_args(dict(lc, params=dict(lc["params"], epsilon=float(ev)))))
+        want = o.ekf_eks(o.LEGACY_TOOLS, *a)
+        assert_bits(out["S_SMOOTH"][:, :, e].T, want["S_SMOOTH"], f"legacy batch eps={ev}")
+        assert_bits(out["P_SMOOTH"][:, :, e].reshape(T, 6, 6).transpose(2, 1, 0), want["P_SMOOTH"], "legacy P_SMOOTH")
+        assert_bits(out["u_opt"][:, :, e].T, want["u_opt"], "legacy u_opt")
