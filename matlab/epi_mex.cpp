@@ -232,6 +232,60 @@ static void cmd_ekf(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) 
   }
 }
 
+// [J0, J1, on_front, I_opt, u_knee] = epi_mex('sweep', params(1xnR struct array), eps(1xnE), u(LxTxnR),
+//     x(TxnR), R(TxnR), s_init(6xnR), Ps_init(6x6xnR), s_final(6xnR), Ps_final(6x6xnR), Q(6x6xnR),
+//     beta_ekf, gamma_ekf, W, x0(3xnR), newcases_hist(T_histxnR), weights(LxTxnR), lean)
+// The batched form of the loop body of Tools/TrainPredictPrescribeNPI.m:421-495 + :624-633 for all
+// regions x all epsilon.  MATLAB's column-major (L x T x nR) is the ABI's per-region [T][L] layout.
+// Outputs: J0, J1, on_front are nE x nR; I_opt 1 x nR (1-based); u_knee L x T_fore x nR.
+static void cmd_sweep(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+  if (nrhs < 17) mexErrMsgIdAndTxt("epi:arg", "sweep: 17 arguments expected");
+  const mwSize *ud = mxGetDimensions(prhs[2]);
+  const int L = (int)ud[0], T = (int)ud[1];
+  const int nR = mxGetNumberOfDimensions(prhs[2]) > 2 ? (int)ud[2] : 1;
+  const int nE = (int)mxGetNumberOfElements(prhs[1]);
+  const int T_hist = (int)mxGetM(prhs[14]);
+  if ((int)mxGetNumberOfElements(prhs[0]) != nR) mexErrMsgIdAndTxt("epi:arg", "sweep: one params struct per region");
+  std::vector<epi_model_params> prm((size_t)nR);
+  for (int r = 0; r < nR; ++r) {
+    // to_params reads element 0 of a struct array: copy element r into a 1x1 view
+    mxArray *one = mxCreateStructMatrix(1, 1, 0, nullptr);
+    const int nf = mxGetNumberOfFields(prhs[0]);
+    for (int f = 0; f < nf; ++f) {
+      const char *name = mxGetFieldNameByNumber(prhs[0], f);
+      mxAddField(one, name);
+      const mxArray *v = mxGetFieldByNumber(prhs[0], r, f);
+      if (v) mxSetField(one, 0, name, mxDuplicateArray(v));
+    }
+    prm[(size_t)r] = to_params(one, L);
+    mxDestroyArray(one);
+  }
+  epi_sweep_args a;
+  std::memset(&a, 0, sizeof a);
+  a.mem = EPI_MEM_HOST; a.n_regions = nR; a.n_eps = nE; a.T = T; a.T_hist = T_hist; a.L = L;
+  a.prm = prm.data(); a.eps = dbl(prhs[1]); a.u = dbl(prhs[2]); a.x = dbl(prhs[3]); a.R = dbl(prhs[4]);
+  a.s_init = dbl(prhs[5]); a.Ps_init = dbl(prhs[6]); a.s_final = dbl(prhs[7]); a.Ps_final = dbl(prhs[8]);
+  a.Q = dbl(prhs[9]); a.beta_ekf = scalar(prhs[10]); a.gamma_ekf = scalar(prhs[11]); a.W = (int)scalar(prhs[12]);
+  a.x0 = dbl(prhs[13]); a.newcases_hist = T_hist > 0 ? dbl(prhs[14]) : nullptr; a.weights = dbl(prhs[15]);
+  a.lean = (int)scalar(prhs[16]);
+  const int Tf = T - T_hist;
+  mxArray *oJ0 = mxCreateDoubleMatrix(nE, nR, mxREAL), *oJ1 = mxCreateDoubleMatrix(nE, nR, mxREAL);
+  mxArray *oF = mxCreateLogicalMatrix(nE, nR);
+  std::vector<int> iopt((size_t)nR);
+  const mwSize kd[3] = {(mwSize)L, (mwSize)Tf, (mwSize)nR};
+  mxArray *oK = mxCreateNumericArray(3, kd, mxDOUBLE_CLASS, mxREAL);
+  a.J0 = mxGetPr(oJ0); a.J1 = mxGetPr(oJ1); a.on_front = (unsigned char *)mxGetLogicals(oF);
+  a.I_opt = iopt.data(); a.u_knee = mxGetPr(oK);
+  check(epi_sweep(ctx(), &a));
+  mxArray *oI = mxCreateDoubleMatrix(1, nR, mxREAL);
+  for (int r = 0; r < nR; ++r) mxGetPr(oI)[r] = (double)(iopt[(size_t)r] + 1);
+  mxArray *o[5] = {oJ0, oJ1, oF, oI, oK};
+  const int want = nlhs > 0 ? nlhs : 1;
+  for (int f = 0; f < 5; ++f) {
+    if (f < want) plhs[f] = o[f]; else mxDestroyArray(o[f]);
+  }
+}
+
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("epi:arg", "first argument must be a command string");
   char cmd[64];
@@ -243,5 +297,6 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   else if (c == "npicost") cmd_npicost(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "pareto") cmd_pareto(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "ekf_eks") cmd_ekf(nlhs, plhs, nrhs - 1, prhs + 1);
+  else if (c == "sweep") cmd_sweep(nlhs, plhs, nrhs - 1, prhs + 1);
   else mexErrMsgIdAndTxt("epi:arg", "unknown command '%s'", cmd);
 }
