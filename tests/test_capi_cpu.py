@@ -159,3 +159,19 @@ def test_gather_costs_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_mex_gateway_type_checks_against_stub_header():
+    """matlab/epi_mex.cpp cannot be built here (no MATLAB/Octave); at least prove it is well-formed C++
+    against the documented MEX API subset (tests/stubs/mex.h) and the real C-ABI header."""
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "stubs"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "matlab", "epi_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every reference signature named in SURVEY 8b has a shim of the same name
+    for name in ("SEIRP", "SEIRPSaturatedResource", "SIAlphaModelEKF", "SIAlphaModelBackwardEKF",
+                 "SIAlphaModelEKFOptControlled", "SIAlphaModelBackwardEKFOptControlled",
+                 "GenericExtendedKalmanFilter", "NewCaseEKFEstimatorWithOptimalNPI", "SIalpha_Controlled",
+                 "SI_Controlled", "NPICost"):
+        txt = open(os.path.join(ROOT, "matlab", name + ".m")).read()
+        assert txt.lstrip().startswith("function") and f"= {name}(" in txt.splitlines()[0], name
