@@ -145,6 +145,33 @@ def shard_regions(n_regions, world_size, rank):
     return lo, min(n_regions, lo + per)
 
 
+def sharded_sweep(compute, inputs, eps, rank, world_size, group=None):
+    """Strong-scaling form of the sweep: rank r takes the contiguous block of regions
+    shard_regions() gives it, runs `compute(local_inputs, eps) -> (J0, J1)` ([n_local, n_eps] torch
+    tensors on the rank's device) and all ranks end up with the full (J0, J1) through the path's single
+    collective.  `compute` is the engine on a GPU box (see bench.py); the CPU tests inject a stand-in."""
+    lo, hi = shard_regions(len(inputs), world_size, rank)
+    J0, J1 = compute(inputs[lo:hi], eps)
+    if world_size == 1:
+        return J0, J1
+    return gather_costs(J0, J1, group=group)
+
+
+def engine_sweep_compute(engine, device=None, lean=False):
+    """compute() for sharded_sweep backed by the engine: fixed-input smoother -> sweep batch -> epi_sweep."""
+    def compute(local_inputs, eps):
+        n_eps = len(eps)
+        if not local_inputs:
+            z = torch.zeros((0, n_eps), dtype=torch.float64, device=device or "cpu")
+            return z, z.clone()
+        S = run_fixed_input(engine, local_inputs)
+        res = run_sweep(engine, sweep_batch(local_inputs, S), np.asarray(eps, dtype=np.float64), want_front=False,
+                        lean=lean)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device or "cpu")
+        return t(res["J0"]), t(res["J1"])
+    return compute
+
+
 def gather_costs(J0, J1, group=None):
     """The path's one collective: all-gather of the per-shard (J0, J1) arrays.
     J0, J1 [n_local_regions, n_eps] torch tensors (CUDA -> NCCL over NVLink; CPU -> gloo).

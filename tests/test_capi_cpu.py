@@ -128,6 +128,37 @@ def test_shard_regions_covers_everything():
                 assert a1 == b0 and a0 <= a1
 
 
+_GLOO_SWEEP_SCRIPT = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np, torch, torch.distributed as dist
+    import cases
+    from oracle import oracle as orc            # stand-in compute for the CPU test (no GPU here)
+    from epidemicmodeling_b200.workloads import sharded_sweep
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    rank = dist.get_rank()
+    inp, eps = cases.sweep_case(n_regions=3, n_eps=4, T_hist=25, T_fore=10)
+
+    def compute(local, eps):
+        J0s, J1s = [], []
+        for r in local:
+            s3, s6, Th = r["setup3"], r["setup6"], r["T_hist"]
+            S = orc.ekf_eks(orc.SIALPHA, r["u_fixed"], r["x"], s3["params"], s3["s_init"], s3["Ps_init"], s3["s_final"],
+                            s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], r["R_v"], 1.0, s3["gamma_ekf"], s3["W"], 1)["S_SMOOTH"]
+            reg = orc.SweepRegion(s6["params"], r["T"], Th, r["u_hist"], r["x"], r["R_v"], s6["s_init"], s6["Ps_init"],
+                                  s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21, S[0, Th - 1], S[1, Th - 1],
+                                  S[2, Th - 1], (S[0, :Th] * S[1, :Th]) * S[2, :Th], r["weights"])
+            j0, j1, _, _, _ = orc.sweep_region(reg, eps)
+            J0s.append(j0); J1s.append(j1)
+        return torch.from_numpy(np.array(J0s).reshape(len(local), len(eps))), torch.from_numpy(np.array(J1s).reshape(len(local), len(eps)))
+
+    g0, g1 = sharded_sweep(compute, inp, eps, rank, 2)
+    f0, f1 = compute(inp, eps)                   # the unsharded answer
+    assert torch.equal(g0, f0) and torch.equal(g1, f1), rank
+    dist.barrier(); dist.destroy_process_group()
+    print("ok", rank)
+""")
+
 _GLOO_SCRIPT = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, {root!r})
@@ -175,3 +206,28 @@ def test_mex_gateway_type_checks_against_stub_header():
                  "SI_Controlled", "NPICost"):
         txt = open(os.path.join(ROOT, "matlab", name + ".m")).read()
         assert txt.lstrip().startswith("function") and f"= {name}(" in txt.splitlines()[0], name
+
+
+def test_sharded_sweep_world_size_2_gloo(tmp_path):
+    """The N > 1 path end to end on CPU: shard regions, compute (oracle stand-in), all-gather (gloo)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "gloo_sweep.py"
+    script.write_text(_GLOO_SWEEP_SCRIPT.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    """No silent fallback: without the built .so the product import path raises."""
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['EPI_B200_LIB'] = %r; "
+            "from epidemicmodeling_b200 import _capi\n"
+            "try:\n    _capi.load()\nexcept ImportError as e:\n    print('RAISED', e)\n" % (ROOT, str(tmp_path / "nope.so")))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert "RAISED" in out.stdout and "no cpu fallback" in out.stdout.lower(), out.stdout + out.stderr
