@@ -588,3 +588,101 @@ def test_ekf_scalar_R_per_trajectory_adaptive_and_legacy_batch(engine):
         assert_bits(out["S_SMOOTH"][:, :, e].T, want["S_SMOOTH"], f"legacy batch eps={ev}")
         assert_bits(out["P_SMOOTH"][:, :, e].reshape(T, 6, 6).transpose(2, 1, 0), want["P_SMOOTH"], "legacy P_SMOOTH")
         assert_bits(out["u_opt"][:, :, e].T, want["u_opt"], "legacy u_opt")
+
+
+# ------------------------------------------------------------------------------ BASELINE full sizes (device memory)
+def test_config2_seirp_ensemble_full_size(engine):
+    """BASELINE config 2: 1M parameter sets x 365 days.  Properties: conservation of s+e+i+r+p
+    (the right-hand sides of SEIRP.m:27-31 sum to zero), final-only mode == last sample; plus an
+    oracle spot check."""
+    import torch
+    B, Kn = 1_000_000, 365
+    rates, ic = syn.seirp_ensemble(B)
+    rd, icd = torch.from_numpy(rates).cuda(), torch.from_numpy(ic).cuda()
+    out = engine.seirp(rd, icd, Kn, 1.0)
+    fin = engine.seirp(rd, icd, Kn, 1.0, out_mode=K.SEIRP_OUT_FINAL)
+    engine.sync()
+    tot = out.sum(dim=0)
+    assert float((tot - 1.0).abs().max()) < 1e-12
+    assert torch.equal(fin, out[:, -1, :])
+    assert bool(torch.isfinite(out).all()) and float(out.min()) > -1e-12
+    o = orc()
+    for b in (0, 31, 255, 256, 499_999, B - 1):
+        want = o.SEIRP(*rates[:, b], *ic[:, b], float(Kn), 1.0)
+        got = out[:, :, b].cpu().numpy()
+        for f in range(5):
+            assert_bits(got[f], want[f][0], f"config2 b={b} f={f}")
+
+
+def test_config3_ekf3_replicates_full_width_sample(engine):
+    """BASELINE config 3 shape (236 regions x replicates x 400 days), 200 replicates per region in device
+    memory (the 10k-replicate run is tools/bench_configs.py): bounds + oracle spot check."""
+    import torch
+    nR, nRep, T = 236, 200, 400
+    inp = syn.sweep_inputs(n_regions=nR, T_hist=T, T_fore=0)
+    b = wl.fixed_input_batch(inp)
+    rng = np.random.default_rng(3)
+    B = nR * nRep
+    clean = np.stack([r["x"] for r in inp])                                   # [nR,T]
+    x = np.maximum(0.0, np.repeat(clean.T[:, :, None], nRep, axis=2) * (1 + 0.05 * rng.standard_normal((T, nR, nRep))))
+    x = np.ascontiguousarray(x.reshape(T, B))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    from epidemicmodeling_b200.engine import params_to_device
+    out = engine.ekf_eks(K.MODEL_SIALPHA, params_to_device(b["prm"], "cuda:0"), dev(b["u"]), dev(x), dev(b["R"]),
+                         dev(b["Q"]), dev(b["s_init"]), dev(b["Ps_init"]), dev(b["s_final"]), dev(b["Ps_final"]),
+                         B=B, T=T, L=b["L"], G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=1.0,
+                         gamma=b["gamma"], W=b["W"], outputs=("S_SMOOTH",), want_status=True)
+    engine.sync()
+    S = out["S_SMOOTH"]
+    assert bool(torch.isfinite(S).all())
+    assert float(S[:, 0].min()) >= 0 and float(S[:, 0].max()) <= 1 and float(S[:, 1].min()) >= 0 and float(S[:, 1].max()) <= 1
+    assert float(S[:, 2].min()) >= 1e-8 and float(S[:, 2].max()) <= 100.0      # StateHardMargins (:27-31)
+    assert int(out["status"].max().item()) == 0
+    o = orc()
+    for bb in (0, 199, 200, 23_456, B - 1):
+        r = inp[bb // nRep]
+        s3 = r["setup3"]
+        want = o.ekf_eks(o.SIALPHA, r["u_fixed"], x[:, bb], s3["params"], s3["s_init"], s3["Ps_init"], s3["s_final"],
+                         s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], r["R_v"], 1.0, s3["gamma_ekf"], s3["W"], 1)
+        assert_bits(S[:, :, bb].cpu().numpy().T, want["S_SMOOTH"], f"config3 b={bb}")
+
+
+def test_config5_monte_carlo_scoring_wide(engine):
+    """BASELINE config 5 shape at 236 regions x 8192 uint8 schedules x 120 days on the device (TMA-staged
+    kernel) + per-region Pareto of the cloud: cost bounds, front idempotence, oracle spot check."""
+    import torch
+    from epidemicmodeling_b200.engine import params_to_device
+    nR, nS, Kn, L = 236, 8192, 120, 12
+    reg = syn.load_regions(nR)
+    B = nR * nS
+    g = torch.Generator(device="cuda").manual_seed(5)
+    u8 = torch.empty((Kn, L, B), dtype=torch.uint8, device="cuda")
+    for j in range(L):
+        u8[:, j, :] = torch.randint(0, int(reg["npi_max"][j]) + 1, (Kn, B), dtype=torch.uint8, device="cuda", generator=g)
+    prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                            alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
+    x0 = np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)])
+    w = np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    res = engine.rollout_cost(params_to_device(prm, "cuda:0"), dev(x0), u8, Kn, L, G=nS, B=B, want_traj=False,
+                              want_cost=True, T_total=Kn, j0_prefix=dev(np.zeros(nR)), j1_prefix=dev(np.zeros(nR)), w=dev(w))
+    J0, J1 = res["J0"].view(nR, nS), res["J1"].view(nR, nS)
+    mask, iopt = engine.pareto(J0, J1)
+    engine.sync()
+    assert bool(torch.isfinite(J0).all()) and bool(torch.isfinite(J1).all()) and float(J0.min()) >= 0
+    wmax = torch.from_numpy(np.array([np.mean(reg["cost_weights"][r] * reg["npi_max"]) for r in range(nR)])).cuda()
+    assert bool((J1 <= wmax[:, None] * (1 + 1e-12)).all())
+    m = mask.bool()
+    assert bool(m.any(dim=1).all())
+    inf = torch.full_like(J0, float("inf"))
+    m2, _ = engine.pareto(torch.where(m, J0, inf), torch.where(m, J1, inf))
+    engine.sync()
+    assert bool(((m2.bool() & m) == m).all())
+    o = orc()
+    uh = u8.cpu().numpy()
+    for bb in (0, 8191, 8192, 1_000_003, B - 1):
+        r = bb // nS
+        s, i, al = o.SIalpha_Controlled(uh[:, :, bb].T.astype(float), *x0[r], reg["npi_max"], 1e-8, 100.0, syn.GAMMA,
+                                        reg["a"][r], reg["b"][r], syn.BETA, 0.0, 0.0, 0.0, Kn, 1.0)
+        j0, j1 = o.NPICost((s * i) * al, uh[:, :, bb].T.astype(float), w[r].T)
+        assert float(res["J0"][bb]) == j0 and float(res["J1"][bb]) == j1, bb
