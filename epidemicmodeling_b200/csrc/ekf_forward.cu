@@ -63,8 +63,12 @@ void launch_group_day(const epi_model_params *prm, const double *u, const double
 // ===========================================================================
 // forward pass
 // ===========================================================================
+#ifndef EPI_FWD_MIN_BLOCKS6
+#define EPI_FWD_MIN_BLOCKS6 8  // m = 6: 32-thread CTAs, 8 per SM = 255 registers (measured best)
+#endif
 template <int MODEL, bool MONITOR, bool TILED>
-__global__ void __launch_bounds__(64) ekf_forward_kernel(const __grid_constant__ EkfParams P) {
+__global__ void __launch_bounds__((model_dim(MODEL) == 6) ? 32 : 64, (model_dim(MODEL) == 6) ? EPI_FWD_MIN_BLOCKS6 : 4)
+ekf_forward_kernel(const __grid_constant__ EkfParams P) {
   constexpr int M = model_dim(MODEL);
   constexpr bool LEG = model_legacy(MODEL);
   constexpr bool SYM = !LEG;

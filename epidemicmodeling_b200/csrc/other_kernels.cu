@@ -324,7 +324,9 @@ EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (i
 EPI_DI double stage_value(const unsigned char *p) { return u32_to_double((unsigned)*p); }
 EPI_DI double stage_value(const double *p) { return *p; }
 
-template <int U_KIND, int SB, int TT>
+// LC: compile-time number of NPIs (12, the OxCGRT shape) or 0 = runtime P.L.
+// SIMPLE: the Monte-Carlo scoring shape -- costs only (no trajectory outputs), no noise array.
+template <int U_KIND, int SB, int TT, int LC, bool SIMPLE>
 __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constant__ RolloutParams P) {
   using U = typename std::conditional<U_KIND == EPI_U_U8, unsigned char, double>::type;
   extern __shared__ __align__(128) unsigned char stage_raw[];  // [2][TT][L][SB] of U
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   const int b = (int)(blk0 + tid);
   const bool active = b < P.B;
   const int nb = (P.B - blk0 < SB) ? (int)(P.B - blk0) : SB;
-  const int K = P.K, L = P.L;
+  const int K = P.K, L = LC ? LC : P.L;
   U *stage_u = reinterpret_cast<U *>(stage_raw);
   const size_t stage_elems = (size_t)TT * L * SB;
   const U *__restrict__ gu = reinterpret_cast<const U *>(P.u) + (size_t)P.u_off + blk0;
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   double S = P.x0[3 * g + 0], I = P.x0[3 * g + 1], A = P.x0[3 * g + 2];
   double sd_s = 0.0, sd_i = 0.0, sd_a = 0.0;
   if (P.noise_std) { sd_s = P.noise_std[3 * g + 0]; sd_i = P.noise_std[3 * g + 1]; sd_a = P.noise_std[3 * g + 2]; }
-  const bool want_cost = P.J0.p != nullptr;
+  const bool want_cost = SIMPLE || (P.J0.p != nullptr);
   double ga[EPI_LMAX], um[EPI_LMAX];  // loop-invariant gamma*a(j), u_max(j)
 #pragma unroll
   for (int j = 0; j < EPI_LMAX; ++j) {
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   double a0 = want_cost && P.j0_prefix ? P.j0_prefix[g] : 0.0;
   double a1 = want_cost && P.j1_prefix ? P.j1_prefix[g] : 0.0;
   const size_t ns = (size_t)P.noise.stride;
-  const double *__restrict__ nz = (P.noise.p && active) ? P.noise.p + P.noise.off + b : nullptr;
+  const double *__restrict__ nz = (!SIMPLE && P.noise.p && active) ? P.noise.p + P.noise.off + b : nullptr;
 
   // weights are per group: when the whole CTA lies in one group they are staged per time tile
   const long long g_first = (P.b0 + blk0) / P.G, g_last = (P.b0 + blk0 + nb - 1) / P.G;
@@ -392,18 +394,21 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
     }
     mbar_wait(&bars[sidx & 1], (unsigned)((sidx >> 1) & 1));
     const U *__restrict__ su = stage_u + (size_t)(sidx & 1) * stage_elems + tid;
-    if (active) {
-      // the input term and the day's weighted cost do not depend on the state: evaluate them
-      // for DQ days at once (independent FMA chains = instruction-level parallelism), then run
-      // the DQ strictly sequential state updates
+    // the input term and the day's weighted cost do not depend on the state: evaluate them for DQ
+    // days at once (independent FMA chains = instruction-level parallelism), then run the DQ
+    // strictly sequential state updates.  FULL = a whole TT-day tile (constant trip counts).
+    auto run_tile = [&](auto full_tag) {
       constexpr int DQ = 4;
-      for (int tq = 0; tq < nt; tq += DQ) {
+      constexpr bool FULL = decltype(full_tag)::value && (TT % DQ == 0);  // no per-day bounds checks
+      const int ntl = FULL ? TT : nt;
+#pragma unroll 1
+      for (int tq = 0; tq < ntl; tq += DQ) {
         double dotq[DQ], cq[DQ];
 #pragma unroll
         for (int q = 0; q < DQ; ++q) {
           dotq[q] = 0.0; cq[q] = 0.0;
           const int tt = tq + q;
-          if (tt < nt) {
+          if (FULL || tt < ntl) {
             const double *wd = w_tiled ? wtile + tt * L
                                : ((want_cost && P.w) ? P.w + ((size_t)g * K + (t0 + tt)) * L : nullptr);
 #pragma unroll
@@ -412,7 +417,7 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
                 const double uj = stage_value(su + (size_t)(tt * L + j) * SB);
                 const double d = um[j] - uj;
                 dotq[q] = (j == 0) ? ga[j] * d : fma(ga[j], d, dotq[q]);
-                if (wd) {
+                if (SIMPLE || wd) {
                   const double wu = wd[j] * uj;
                   cq[q] = (j == 0) ? wu : (cq[q] + wu);
                 }
@@ -423,10 +428,10 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
 #pragma unroll
         for (int q = 0; q < DQ; ++q) {
           const int tt = tq + q;
-          if (tt < nt) {
+          if (FULL || tt < ntl) {
             const int t = t0 + tt;
             double n_s = 0.0, n_i = 0.0, n_a = 0.0;
-            if (nz) {
+            if (!SIMPLE && nz) {
               n_s = nz[((size_t)t * 3 + 0) * ns];
               n_i = nz[((size_t)t * 3 + 1) * ns];
               n_a = nz[((size_t)t * 3 + 2) * ns];
@@ -436,9 +441,11 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
             const double In = mmax(0.0, mmin(1.0, I + dt * ((asi - beta * I) + n_i * sd_i)));
             const double An = mmax(amin, mmin(amax, A + dt * (((((-gamma) * A) + gamma * bb) + dotq[q]) + n_a * sd_a)));
             S = Sn; I = In; A = An;
-            if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
-            if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
-            if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
+            if (!SIMPLE) {
+              if (P.s.p) P.s.p[(size_t)t * P.s.stride + P.s.off + b] = S;
+              if (P.i.p) P.i.p[(size_t)t * P.i.stride + P.i.off + b] = I;
+              if (P.alpha.p) P.alpha.p[(size_t)t * P.alpha.stride + P.alpha.off + b] = A;
+            }
             if (want_cost) {
               a0 += (S * I) * A;  // s.*i.*alpha (:493)
               a1 += cq[q];
@@ -446,6 +453,10 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
           }
         }
       }
+    };
+    if (active) {
+      if (nt == TT) run_tile(std::true_type{});
+      else run_tile(std::false_type{});
     }
     __syncthreads();  // everyone is done reading this buffer
     if (tid < 32 && sidx + 2 < n_stages) issue(sidx + 2);
@@ -466,9 +477,17 @@ static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
       (((size_t)p.u_off * esz) & 15) || ((size_t)p.u & 15))
     return false;
   const size_t smem = (size_t)2 * TT * p.L * SB * esz;
-  auto kern = rollout_staged_kernel<U_KIND, SB, TT>;
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  kern<<<(p.B + SB - 1) / SB, SB, smem, st>>>(p);
+  const unsigned grid = (unsigned)((p.B + SB - 1) / SB);
+  const bool simple = p.J0.p && p.w && !p.noise.p && !p.s.p && !p.i.p && !p.alpha.p;
+#define EPI_LAUNCH_STAGED(LC, SIMPLE)                                                              \
+  do {                                                                                             \
+    auto kern = rollout_staged_kernel<U_KIND, SB, TT, LC, SIMPLE>;                                 \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    kern<<<grid, SB, smem, st>>>(p);                                                               \
+  } while (0)
+  if (p.L == 12) { if (simple) EPI_LAUNCH_STAGED(12, true); else EPI_LAUNCH_STAGED(12, false); }
+  else           { if (simple) EPI_LAUNCH_STAGED(0, true);  else EPI_LAUNCH_STAGED(0, false); }
+#undef EPI_LAUNCH_STAGED
   return true;
 }
 
