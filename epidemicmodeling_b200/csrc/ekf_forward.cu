@@ -163,26 +163,37 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
           if (i >= 3) acc = acc + Pm(i, j);
           MP.at(i, j) = acc;
         }
-      if (LEG) {
+      // the m^2 quotients by gamma: fast exact-division path for the whole block, true divisions
+      // only if some numerator left the safe exponent range (checked once, after the block)
+      auto covariance_update = [&](auto exact_tag) {
+        constexpr bool EXACT = decltype(exact_tag)::value;
+        ExpRange rng;
+        if (LEG) {
 #pragma unroll
-        for (int i = 0; i < M; ++i)
+          for (int i = 0; i < M; ++i)
 #pragma unroll
-          for (int j = 0; j < M; ++j) Pp.at(i, j) = div_by(MP(i, j), by_gamma);  // legacy :64
-      } else {
-        // :127 Joseph form, :138 symmetrisation
+            for (int j = 0; j < M; ++j)
+              Pp.at(i, j) = EXACT ? MP(i, j) / gamma : div_fast(MP(i, j), by_gamma, rng);  // legacy :64
+        } else {
+          // :127 Joseph form, :138 symmetrisation
 #pragma unroll
-        for (int i = 0; i < M; ++i)
+          for (int i = 0; i < M; ++i)
 #pragma unroll
-          for (int j = i; j < M; ++j) {
-            double mij = fma(MP(i, 2), Mx[j][2], fma(MP(i, 1), Mx[j][1], MP(i, 0) * Mx[j][0]));
-            if (j >= 3) mij = mij + MP(i, j);
-            double mji = fma(MP(j, 2), Mx[i][2], fma(MP(j, 1), Mx[i][1], MP(j, 0) * Mx[i][0]));
-            if (i >= 3) mji = mji + MP(j, i);
-            const double pij = div_by(mij + (K[i] * Rk) * K[j], by_gamma);
-            const double pji = div_by(mji + (K[j] * Rk) * K[i], by_gamma);
-            Pp.at(i, j) = (pij + pji) / 2.0;
-          }
-      }
+            for (int j = i; j < M; ++j) {
+              double mij = fma(MP(i, 2), Mx[j][2], fma(MP(i, 1), Mx[j][1], MP(i, 0) * Mx[j][0]));
+              if (j >= 3) mij = mij + MP(i, j);
+              double mji = fma(MP(j, 2), Mx[i][2], fma(MP(j, 1), Mx[i][1], MP(j, 0) * Mx[i][0]));
+              if (i >= 3) mji = mji + MP(j, i);
+              const double nij = mij + (K[i] * Rk) * K[j];
+              const double nji = mji + (K[j] * Rk) * K[i];
+              const double pij = EXACT ? nij / gamma : div_fast(nij, by_gamma, rng);
+              const double pji = EXACT ? nji / gamma : div_fast(nji, by_gamma, rng);
+              Pp.at(i, j) = (pij + pji) / 2.0;
+            }
+        }
+        return by_gamma.ok && rng.safe();
+      };
+      if (!covariance_update(std::false_type{})) covariance_update(std::true_type{});
 #pragma unroll
       for (int i = 0; i < M; ++i) sp[i] = s[i] + K[i] * innov;  // :129
     } else {  // :131-134

@@ -50,6 +50,21 @@ EPI_DI InvDiv make_invdiv(double b) {
   d.ok = (e - 923u) <= 200u;  // 2^-100 <= |b| <= 2^100 (excludes 0, denormals, inf, NaN)
   return d;
 }
+// Batch form: run many quotients by the same divisor on the fast path unconditionally while
+// tracking the exponent range of the numerators; the caller re-does the whole block with true
+// divisions in the (rare) case the range check fails.  No per-quotient branch.
+struct ExpRange {
+  unsigned lo = 2047u, hi = 0u;
+  EPI_DI bool safe() const { return lo >= 123u && hi <= 1923u; }  // every |a| in [2^-900, 2^900]
+};
+EPI_DI double div_fast(double a, const InvDiv &d, ExpRange &r) {
+  const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+  r.lo = min(r.lo, e);
+  r.hi = max(r.hi, e);
+  const double q0 = a * d.y;
+  const double rem = fma(-q0, d.b, a);
+  return fma(rem, d.y, q0);
+}
 EPI_DI double div_by(double a, const InvDiv &d) {
   const double q0 = a * d.y;
   const double r = fma(-q0, d.b, a);
