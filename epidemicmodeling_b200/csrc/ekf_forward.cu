@@ -147,8 +147,15 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
       const double S0 = fma(CP[2], C[2], fma(CP[1], C[1], CP[0] * C[0]));
       const double denom = S0 + gamma * Rk;  // :124 (+ Gsp + Gvp = 0)
       const InvDiv by_denom = make_invdiv(denom);
+      {
+        ExpRange rng;
 #pragma unroll
-      for (int i = 0; i < M; ++i) K[i] = div_by(PCt[i], by_denom);
+        for (int i = 0; i < M; ++i) K[i] = div_fast(PCt[i], by_denom, rng);
+        if (!(by_denom.ok && rng.safe())) {
+#pragma unroll
+          for (int i = 0; i < M; ++i) K[i] = PCt[i] / denom;
+        }
+      }
       double Mx[M][3];  // I - K*C, columns 0..2 (columns 3.. are identity)
 #pragma unroll
       for (int i = 0; i < M; ++i)
