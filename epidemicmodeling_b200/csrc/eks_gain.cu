@@ -11,8 +11,31 @@
 namespace epi {
 
 #ifndef EPI_GAIN_MIN_BLOCKS
-#define EPI_GAIN_MIN_BLOCKS 3
+#define EPI_GAIN_MIN_BLOCKS 4
 #endif
+
+// A_k = df/ds at S_PLUS(:,k)  (GenericExtendedKalmanFilter.m:206)
+template <int MODEL, bool TILED>
+EPI_DI void gain_jacobian(const TrajIn &in, const Tape<TILED> &tSp, int pos, int L, Mat<model_dim(MODEL), false> &A) {
+  constexpr int M = model_dim(MODEL);
+  const ModelConsts mc = load_consts(in.prm);
+  double sp[M];
+  {
+    const double *__restrict__ d = tSp.at_day(pos);
+#pragma unroll
+    for (int i = 0; i < M; ++i) sp[i] = d[tSp.f(i)];
+  }
+  double a25 = 0.0;
+  if (M == 6) {
+    const double pre = in.dot_grp ? __ldg(in.dot_grp + pos) : __longlong_as_double(0x7ff8000000000000ll);
+    if (!(pre == pre)) {
+      const InputPass ip = input_pass<MODEL, true, false>(mc, in.eps, sp[M - 1], in.u + (size_t)pos * in.u_ts,
+                                                          in.u_js, L, nullptr, 0, nullptr);
+      a25 = ip.a25;
+    }
+  }
+  state_jacobian<MODEL>(mc, in.eps, sp, a25, A);
+}
 
 template <int MODEL, bool TILED>
 __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(const __grid_constant__ EkfParams P) {
@@ -34,63 +57,91 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
   const int pos = REV ? (T - 1 - k) : k;
   const int posn = REV ? (T - 2 - k) : (k + 1);
   const TrajIn in = traj_inputs(P, b, M);
-  const ModelConsts mc = load_consts(in.prm);
 
   const Tape<TILED> tSp = make_tape<TILED>(P.S_PLUS, M, T - k0, b, k0);
   const Tape<TILED> tPm = make_tape<TILED>(P.P_MINUS, PF, T - k0, b, k0), tPp = make_tape<TILED>(P.P_PLUS, PF, T - k0, b, k0);
   const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1 - k0, b, k0);
 
-  double sp[M];
-  {
-    const double *__restrict__ d = tSp.at_day(pos);
-#pragma unroll
-    for (int i = 0; i < M; ++i) sp[i] = d[tSp.f(i)];
-  }
-  double a25 = 0.0;
-  if (M == 6) {
-    const double pre = in.dot_grp ? __ldg(in.dot_grp + pos) : __longlong_as_double(0x7ff8000000000000ll);
-    if (!(pre == pre)) {
-      const InputPass ip = input_pass<MODEL, true, false>(mc, in.eps, sp[M - 1], in.u + (size_t)pos * in.u_ts,
-                                                          in.u_js, L, nullptr, 0, nullptr);
-      a25 = ip.a25;
-    }
-  }
-  Mat<M, false> A;
-  state_jacobian<MODEL>(mc, in.eps, sp, a25, A);  // :206
-
-  Mat<M, false> Jm;
+  // rotation stack of pinv_sym (generic models only)
+  __shared__ double rot_stack[LEG ? 1 : RotStack<M, 128>::SMEM_WORDS];
+  Mat<M, false> A, Jm;
   int rank = M;
-  bool bad = false;
+  bool bad = false, stored = false;
   if (!LEG) {
     Mat<M, true> Pn, X;
     tape_load_cov<M, true, TILED, PACKED>(Pn, tPm, tPm.at_day(posn));
+    {
+      // P+ and S+ are read only after the eigen-iteration: pull their lines into L2 now
+      const double *__restrict__ dpp = tPp.at_day(pos);
+#pragma unroll
+      for (int q = 0; q < PF; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(dpp + tPp.f(q)));
+      const double *__restrict__ dsp = tSp.at_day(pos);
+#pragma unroll
+      for (int q = 0; q < M; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(dsp + tSp.f(q)));
+    }
 #pragma unroll
     for (int q = 0; q < Mat<M, true>::N; ++q) bad |= !(fabs(Pn.v[q]) <= 1.79769313486231570815e308);  // :211
     if (bad) {
 #pragma unroll
       for (int q = 0; q < MM; ++q) Jm.v[q] = 0.0;  // :213
     } else {
-      VRegs<M> v;  // eigenvectors in registers (a shared-memory V was measured slower: 9.1 vs 8.0 ms)
-      rank = pinv_sym<M>(Pn, X, v);
-      Mat<M, true> Pp;
-      tape_load_cov<M, true, TILED, PACKED>(Pp, tPp, tPp.at_day(pos));
-      Mat<M, false> PAt;
+#ifdef EPI_GAIN_SKIP_PINV  // experiment: cost of everything but the eigen-iteration
+      X = Pn;
+#else
+      rank = pinv_sym<M, 128>(Pn, X, rot_stack + threadIdx.x);
+#endif
+      // the state Jacobian is evaluated AFTER the eigen-iteration so that neither its entries nor
+      // the model constants are live (or spilled) across it
+      gain_jacobian<MODEL, TILED>(in, tSp, pos, L, A);  // :206
+      // J = (P+ A') X row by row (:215): only one row of P+ and of P+ A' is live at a time, and
+      // the finished row goes straight to the tape (row-major J(i,l) = field i*M + l)
+      const double *__restrict__ dp = tPp.at_day(pos);
+      double *__restrict__ dj = tJ.at_day(k);
+      // row i of the symmetric P+ page for run-time i: element (i,l) is field l*M + i of a full
+      // page; of a packed page it is field  i*M - i(i-1)/2 - i + l  for l >= i  and
+      // l*M - l(l-1)/2 - l + i  for l < i  -- one run-time base each, the rest immediates
+      auto load_row = [&](int i, double(&row)[M]) {
+        const double *__restrict__ up = dp + tPp.f(PACKED ? (i * M - (i * (i - 1)) / 2 - i) : i);
+        const double *__restrict__ lw = dp + tPp.f(i);
 #pragma unroll
-      for (int i = 0; i < M; ++i)
-#pragma unroll
-        for (int j = 0; j < M; ++j) PAt.at(i, j) = mul_X_At_ij<M>(Pp, A, i, j);
-#pragma unroll
-      for (int i = 0; i < M; ++i)
-#pragma unroll
-        for (int j = 0; j < M; ++j) {  // :215
-          double acc = PAt(i, 0) * X(0, j);
-#pragma unroll
-          for (int l = 1; l < M; ++l) acc = fma(PAt(i, l), X(l, j), acc);
-          Jm.at(i, j) = acc;
+        for (int l = 0; l < M; ++l) {
+          if (PACKED) row[l] = (l < i) ? lw[tPp.f(l * M - (l * (l - 1)) / 2 - l)] : up[tPp.f(l)];
+          else row[l] = up[tPp.f(l * M)];
         }
+      };
+      double prow[M];
+      load_row(0, prow);
+#pragma unroll 1  // rolled: the row body is ~100 instructions, 6 copies of it would not fit the i-cache budget
+      for (int i = 0; i < M; ++i) {
+        double pnext[M], pat[M];
+        load_row(i + 1 < M ? i + 1 : i, pnext);  // next row's loads in flight during this row's products
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          double acc = 0.0;
+          bool first = true;
+#pragma unroll
+          for (int l = 0; l < M; ++l)
+            if (a_nz(M, j, l)) {
+              acc = first ? prow[l] * A(j, l) : fma(prow[l], A(j, l), acc);
+              first = false;
+            }
+          pat[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          double acc = pat[0] * X(0, j);
+#pragma unroll
+          for (int l = 1; l < M; ++l) acc = fma(pat[l], X(l, j), acc);
+          dj[tJ.f(i * M + j)] = acc;
+        }
+#pragma unroll
+        for (int l = 0; l < M; ++l) prow[l] = pnext[l];
+      }
+      stored = true;
     }
   } else {
     // legacy :132   J = (P+ A') / P-   via LU with partial pivoting of (P-)'
+    gain_jacobian<MODEL, TILED>(in, tSp, pos, L, A);  // :206
     Mat<M, false> Pp, lu, rhs;
     tape_load_cov<M, false, TILED, false>(Pp, tPp, tPp.at_day(pos));
     {
@@ -111,7 +162,7 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 #pragma unroll
       for (int j = 0; j < M; ++j) Jm.at(i, j) = rhs(j, i);
   }
-  {
+  if (!stored) {
     double *__restrict__ d = tJ.at_day(k);
 #pragma unroll
     for (int q = 0; q < MM; ++q) d[tJ.f(q)] = Jm.v[q];  // row-major J(i,l) = field i*M + l

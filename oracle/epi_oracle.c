@@ -175,45 +175,101 @@ static double eps_of(double x) {
   return v.d;
 }
 
-#define ORC_JACOBI_MAXSWEEP 30
+#define ORC_JACOBI_MAXSWEEP 16
 static const double ORC_JACOBI_REL = 2.168404344971009e-19; /* 2^-62 */
 
-/* Threshold cyclic Jacobi (row-cyclic order p<q) on the symmetric matrix whose
- * upper triangle is A (column-major mxm).  lambda_i = diagonal after
- * convergence, eigenvectors = columns of V.  A pair (p,q) is rotated iff
- * |a_pq| > 2^-62 * max_p|a_pp| (recomputed at each sweep start); the iteration
- * stops when no pair qualifies (or after 30 sweeps).
- * pinv = sum_i [|lambda_i| > tol] v_i (1/lambda_i) v_i',
- * tol = m * eps(max|lambda|)   (MATLAB pinv's default tolerance). */
+/* Pair order of one Jacobi sweep: "sets" of index-disjoint pairs (round-robin
+ * tournament).  Rotations of one set commute exactly (their angles read
+ * a_pp, a_qq, a_pq of disjoint index pairs), which is what lets the CUDA kernel
+ * compute the three angles of a 6x6 set side by side; the APPLICATION order is
+ * still the listed order, pair by pair, and a pair (p,q) is rotated as listed
+ * (p > q occurs: the table is the circle method -- pairs at positions (0,1),
+ * (2,3), (4,5), then positions 1..5 rotate -- which the kernel executes as one
+ * rolled loop).  m = 2 and m = 3 have one pair per set (m = 3: the classical
+ * row-cyclic order). */
+static const int ORC_JSETS6[5][3][2] = {{{0, 1}, {2, 3}, {4, 5}}, {{0, 3}, {1, 5}, {2, 4}},
+                                        {{0, 5}, {3, 4}, {1, 2}}, {{0, 4}, {5, 2}, {3, 1}},
+                                        {{0, 2}, {4, 1}, {5, 3}}};
+static const int ORC_JSETS3[3][1][2] = {{{0, 1}}, {{0, 2}}, {{1, 2}}};
+static const int ORC_JSETS2[1][1][2] = {{{0, 1}}};
+
+/* Rotation annihilating a_pq (apq != 0), tan(2 phi) = apq / d with d = (aqq - app)/2:
+ *   r = sqrt(d^2 + apq^2),  t = sgn(d) apq / (|d| + r)  (sgn(0) = +1),
+ *   c = sqrt((|d| + r) / (2 r)),  s = t c
+ * -- the same angle as the textbook theta = d/apq, t = sgn(theta)/(|theta| + sqrt(theta^2+1)),
+ * c = 1/sqrt(t^2+1), with 2 divisions + 2 square roots on a dependency chain of 3 instead of
+ * 3 + 2 on a chain of 5.  When d^2 + apq^2 leaves [2^-900, 2^900] (squares about to
+ * under/overflow) the textbook form, which cannot overflow, is used instead. */
+static void jacobi_angle(double app, double aqq, double apq, double *t_, double *c_, double *s_) {
+  double d = 0.5 * (aqq - app);
+  double r2 = fma(d, d, apq * apq);
+  double t, c;
+  if (r2 > 1.1830521861667747e-271 && r2 < 8.452712498170644e+270) { /* 2^-900 .. 2^900 */
+    double ad = fabs(d);
+    double r = sqrt(r2);
+    double den = ad + r;
+    t = apq / den;
+    if (d < 0.0) t = -t;
+    c = sqrt(den / (r + r));
+  } else {
+    double theta = d / apq;
+    double at = fabs(theta);
+    t = 1.0 / (at + sqrt(at * at + 1.0));
+    if (theta < 0.0) t = -t;
+    c = 1.0 / sqrt(t * t + 1.0);
+  }
+  *t_ = t; *c_ = c; *s_ = t * c;
+}
+
+/* Threshold Jacobi on the symmetric matrix whose upper triangle is A
+ * (column-major mxm), pairs in the set order above.  A pair (p,q) is ACTIVE iff
+ * |a_pq| > 2^-62 * max_p|a_pp| (threshold recomputed at each sweep start); the
+ * iteration stops when no pair is active at a sweep start (or after 16 sweeps).
+ * A set with no active pair is skipped; in an executed set every pair is
+ * rotated, the idle ones by the identity (t = 0, c = 1, s = 0) -- that changes
+ * no value (at most the sign of a zero) and makes the set branch-free in the
+ * kernel.  lambda_i = diagonal after convergence; the eigenvector matrix
+ * V = R_1 R_2 ... R_n (R_k: plane rotation with R_pp = R_qq = c, R_pq = s,
+ * R_qp = -s) is never formed:
+ *   pinv = V W V' = R_1 ( ... (R_n W R_n') ... ) R_1',   W = diag([|lambda_i| > tol] / lambda_i),
+ *   tol = m * eps(max|lambda|)   (MATLAB pinv's default tolerance)
+ * is evaluated by REPLAYING the recorded rotations, last first, as two-sided
+ * updates of the symmetric X (30 flops per rotation instead of 24 for V plus
+ * the m^3 products; and the kernel needs no m x m eigenvector registers). */
 int orc_pinv_sym(const double *Ain, int m, double *X, int *rank) {
-  double a[MM][MM], v[MM][MM];
+  double a[MM][MM];
+  struct { int p, q; double c, s; } rec[ORC_JACOBI_MAXSWEEP * MM * (MM - 1) / 2];
+  int n_rec = 0;
   for (int i = 0; i < m; ++i)
-    for (int j = 0; j < m; ++j) {
-      a[i][j] = (i <= j) ? Ain[j * m + i] : Ain[i * m + j];
-      v[i][j] = (i == j) ? 1.0 : 0.0;
-    }
+    for (int j = 0; j < m; ++j) a[i][j] = (i <= j) ? Ain[j * m + i] : Ain[i * m + j];
+  const int (*sets)[2] = m == 6 ? &ORC_JSETS6[0][0] : m == 3 ? &ORC_JSETS3[0][0] : m == 2 ? &ORC_JSETS2[0][0] : NULL;
+  const int n_set = m == 6 ? 3 : 1, n_sets = m == 6 ? 5 : m == 3 ? 3 : 1;
   int sweep = 0;
-  for (; sweep < ORC_JACOBI_MAXSWEEP; ++sweep) {
+  for (; sets && sweep < ORC_JACOBI_MAXSWEEP; ++sweep) {
     double dmax = 0.0, offmax = 0.0;
     for (int p = 0; p < m; ++p) dmax = mmax(dmax, fabs(a[p][p]));
     for (int p = 0; p < m; ++p)
       for (int q = p + 1; q < m; ++q) offmax = mmax(offmax, fabs(a[p][q]));
     double thr = dmax * ORC_JACOBI_REL;
     if (!(offmax > thr)) break;
-    for (int p = 0; p < m - 1; ++p)
-      for (int q = p + 1; q < m; ++q) {
-        double apq = a[p][q];
-        if (!(fabs(apq) > thr)) continue;
-        double app = a[p][p], aqq = a[q][q];
-        double theta = (0.5 * (aqq - app)) / apq;
-        double at = fabs(theta);
-        double t = 1.0 / (at + sqrt(at * at + 1.0));
-        if (theta < 0.0) t = -t;
-        double c = 1.0 / sqrt(t * t + 1.0);
-        double s = t * c;
+    for (int st = 0; st < n_sets; ++st) {
+      int act[3], any_act = 0;
+      double tt[3], cc[3], ss[3];
+      for (int i = 0; i < n_set; ++i) { /* the set's angles read disjoint entries */
+        const int p = sets[st * n_set + i][0], q = sets[st * n_set + i][1];
+        act[i] = fabs(a[p][q]) > thr;
+        any_act |= act[i];
+        tt[i] = 0.0; cc[i] = 1.0; ss[i] = 0.0;
+        if (act[i]) jacobi_angle(a[p][p], a[q][q], a[p][q], &tt[i], &cc[i], &ss[i]);
+      }
+      if (!any_act) continue;
+      for (int i = 0; i < n_set; ++i) {
+        const int p = sets[st * n_set + i][0], q = sets[st * n_set + i][1];
+        const double t = tt[i], c = cc[i], s = ss[i];
+        double app = a[p][p], aqq = a[q][q], apq = a[p][q];
         a[p][p] = app - t * apq;
         a[q][q] = aqq + t * apq;
-        a[p][q] = 0.0; a[q][p] = 0.0;
+        if (act[i]) { a[p][q] = 0.0; a[q][p] = 0.0; }
         for (int r = 0; r < m; ++r) {
           if (r != p && r != q) {
             double g = a[r][p], h = a[r][q];
@@ -223,30 +279,43 @@ int orc_pinv_sym(const double *Ain, int m, double *X, int *rank) {
             a[r][q] = hp; a[q][r] = hp;
           }
         }
-        for (int r = 0; r < m; ++r) {
-          double g = v[r][p], h = v[r][q];
-          v[r][p] = fma(c, g, -(s * h));
-          v[r][q] = fma(s, g, c * h);
-        }
+        rec[n_rec].p = p; rec[n_rec].q = q; rec[n_rec].c = c; rec[n_rec].s = s;
+        ++n_rec;
       }
+    }
   }
   double lmax = 0.0;
   for (int i = 0; i < m; ++i) lmax = mmax(lmax, fabs(a[i][i]));
   double tol = (double)m * eps_of(lmax);
-  double w[MM];
+  double x[MM][MM];
   int rk = 0;
   for (int i = 0; i < m; ++i) {
     int keep = fabs(a[i][i]) > tol;
-    w[i] = keep ? 1.0 / a[i][i] : 0.0;
+    for (int j = 0; j < m; ++j) x[i][j] = 0.0;
+    x[i][i] = keep ? 1.0 / a[i][i] : 0.0;
     rk += keep;
   }
-  for (int r = 0; r < m; ++r)
-    for (int c2 = r; c2 < m; ++c2) {
-      double acc = 0.0;
-      for (int i = 0; i < m; ++i) acc = fma(v[r][i] * w[i], v[c2][i], acc);
-      X[c2 * m + r] = acc;
-      X[r * m + c2] = acc;
+  for (int k = n_rec - 1; k >= 0; --k) { /* X <- R_k X R_k' */
+    const int p = rec[k].p, q = rec[k].q;
+    const double c = rec[k].c, s = rec[k].s;
+    for (int r = 0; r < m; ++r) {
+      if (r != p && r != q) {
+        double g = x[r][p], h = x[r][q];
+        double gp = fma(c, g, s * h);
+        double hp = fma(c, h, -(s * g));
+        x[r][p] = gp; x[p][r] = gp;
+        x[r][q] = hp; x[q][r] = hp;
+      }
     }
+    double xpp = x[p][p], xpq = x[p][q], xqq = x[q][q];
+    double u1 = fma(c, xpp, s * xpq), u2 = fma(c, xpq, s * xqq);       /* (R X)(p,p), (R X)(p,q) */
+    double w1 = fma(c, xpq, -(s * xpp)), w2 = fma(c, xqq, -(s * xpq)); /* (R X)(q,p), (R X)(q,q) */
+    x[p][p] = fma(c, u1, s * u2);
+    x[p][q] = fma(c, u2, -(s * u1)); x[q][p] = x[p][q];
+    x[q][q] = fma(c, w2, -(s * w1));
+  }
+  for (int i = 0; i < m; ++i)
+    for (int j = 0; j < m; ++j) X[j * m + i] = x[i][j];
   if (rank) *rank = rk;
   return sweep;
 }
