@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <utility>
+#include <cstdlib>
 #include <vector>
 
 #include "epi_device.cuh"
@@ -843,6 +844,18 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       p.T_hist = a->T_hist;
       if (u_fore_dev) p.u_fore = TArr{u_fore_dev, B, b0};
       p.P_first = w.traj_out(a->P_first, MM, B, b0, nb);
+      {
+        // few-wave batches: time-segmented persistent forward launch (no idle tail)
+        static int slots6 = 0;
+        if (!slots6) slots6 = forward_resident_slots6();
+        const long long tiles = (nb + 31) / 32;
+        p.fwd_segments = a->beta_ekf == 1.0 ? forward_segments(tiles, slots6) : 1;
+        if (const char *e = getenv("EPI_FWD_SEGMENTS")) p.fwd_segments = atoi(e);  // tuning experiments
+        if (p.fwd_segments > 1) {
+          p.fwd_sync = (int *)w.dalloc((size_t)(tiles + 1) * sizeof(int));
+          CK(cudaMemsetAsync(p.fwd_sync, 0, (size_t)(tiles + 1) * sizeof(int), c->stream));
+        }
+      }
       {
         PhaseScope ph(c, "ekf_forward");
         launch_ekf_forward(p, c->stream);

@@ -11,7 +11,13 @@
 // (tiled scratch: all offsets are instruction immediates).
 #include <type_traits>
 
+#include <cstdlib>
 #include "ekf_common.cuh"
+#ifdef EPI_FWD_NO_STORE  // experiment: cost of the tape stores (results are garbage)
+#define EPI_FWD_STORE_COND (pos >= k0 && s[0] == 123.456)
+#else
+#define EPI_FWD_STORE_COND (pos >= k0)
+#endif
 
 namespace epi {
 
@@ -63,22 +69,19 @@ void launch_group_day(const epi_model_params *prm, const double *u, const double
 // ===========================================================================
 // forward pass
 // ===========================================================================
-#ifndef EPI_FWD_MIN_BLOCKS6
-#define EPI_FWD_MIN_BLOCKS6 8  // m = 6: 32-thread CTAs, 8 per SM = 255 registers (measured best; see DESIGN.md)
-#endif
+// Days [k_begin, k_end) of trajectory b.  k_begin == 0 starts from the initial conditions, a later
+// start resumes from the a-priori page (S_MINUS, P_MINUS) of day k_begin that the previous segment
+// left on the tape -- without the innovation monitor that page IS the whole filter state.
 template <int MODEL, bool MONITOR, bool TILED>
-__global__ void __launch_bounds__((model_dim(MODEL) == 6) ? 32 : 64, (model_dim(MODEL) == 6) ? EPI_FWD_MIN_BLOCKS6 : 4)
-ekf_forward_kernel(const __grid_constant__ EkfParams P) {
+EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, const int k_end, double *win) {
   constexpr int M = model_dim(MODEL);
   constexpr bool LEG = model_legacy(MODEL);
   constexpr bool SYM = !LEG;
   constexpr bool REV = model_flipped(MODEL);
   constexpr int MM = M * M;
   constexpr int PF = (SYM && TILED) ? M * (M + 1) / 2 : MM;
-  extern __shared__ double win[];  // MONITOR: [3][W][blockDim.x]
   using TmpMat = Mat<M, false>;  // (a shared-memory backing, SMat, was tried: no register relief)
 
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   const TrajIn in = traj_inputs(P, b, M);
   const ModelConsts mc = load_consts(in.prm);
@@ -92,7 +95,19 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
 
   double s[M];
   Mat<M, SYM> Pm;  // P(k|k-1)
-  if (P.init_per_traj) {
+  if (k_begin > 0) {
+    // resume: written by another CTA of this launch (possibly on another SM) => bypass L1
+    const int pos = REV ? (T - 1 - k_begin) : k_begin;
+    const double *__restrict__ d = tSm.at_day(pos);
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = __ldcg(d + tSm.f(i));
+    const double *__restrict__ dP = tPm.at_day(pos);
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j)
+        if (!SYM || j >= i) Pm.at(i, j) = __ldcg(dP + tPm.f((SYM && TILED) ? Mat<M, true>::idx(i, j) : (j * M + i)));
+  } else if (P.init_per_traj) {
     const double *si = P.s_init_t.p + P.s_init_t.off + b;
 #pragma unroll
     for (int i = 0; i < M; ++i) s[i] = si[(size_t)i * P.s_init_t.stride];
@@ -110,10 +125,10 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
   double R_over = 0.0;        // adapted R for the next step (:184)
   bool has_over = false;
 
-  for (int k = 0; k < T; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const int pos = REV ? (T - 1 - k) : k;
     // :100-101 store the a-priori estimate
-    if (pos >= k0) {
+    if (EPI_FWD_STORE_COND) {
       double *__restrict__ d = tSm.at_day(pos);
 #pragma unroll
       for (int i = 0; i < M; ++i) d[tSm.f(i)] = s[i];
@@ -265,7 +280,7 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
     for (int i = 0; i < M; ++i) s[i] = sn[i];
 
     // :167-169
-    if (pos >= k0) {
+    if (EPI_FWD_STORE_COND) {
       double *__restrict__ d = tSp.at_day(pos);
 #pragma unroll
       for (int i = 0; i < M; ++i) d[tSp.f(i)] = sp[i];
@@ -311,6 +326,59 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
       R_over = Rk;
     }
   }
+  if (k_end < T) {  // hand the a-priori page of day k_end to the segment that continues
+    const int pos = REV ? (T - 1 - k_end) : k_end;
+    double *__restrict__ d = tSm.at_day(pos);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d[tSm.f(i)] = s[i];
+    tape_store_cov<M, SYM, TILED>(Pm, tPm, tPm.at_day(pos));
+  }
+}
+
+#ifndef EPI_FWD_MIN_BLOCKS6
+#define EPI_FWD_MIN_BLOCKS6 8  // m = 6: 32-thread CTAs, 8 per SM = 255 registers (measured best; see DESIGN.md)
+#endif
+template <int MODEL, bool MONITOR, bool TILED>
+__global__ void __launch_bounds__((model_dim(MODEL) == 6) ? 32 : 64, (model_dim(MODEL) == 6) ? EPI_FWD_MIN_BLOCKS6 : 4)
+ekf_forward_kernel(const __grid_constant__ EkfParams P) {
+  extern __shared__ double win[];  // MONITOR: [3][W][blockDim.x]
+  forward_days<MODEL, MONITOR, TILED>(P, blockIdx.x * blockDim.x + threadIdx.x, 0, P.T, win);
+}
+
+// Persistent, time-segmented form for batches of only a few waves (the 236 x 250 sweep is
+// 1844 warps on 1184 resident slots: 1.56 waves, i.e. the second wave leaves 44 % of the slots
+// idle).  The T days of every 32-trajectory tile are cut into P.fwd_segments segments; CTAs (one
+// warp each) draw (segment, tile) items segment-major from an atomic counter, so a finished slot
+// continues with the next segment of some other tile instead of idling.  An item waits for its
+// predecessor (same tile, previous segment) through a per-tile progress word; predecessors
+// always have a lower item number, so they are running or done and the wait cannot deadlock.
+// sync[0] = item counter, sync[1 + tile] = segments of that tile finished (zeroed by the host).
+template <int MODEL, bool TILED>
+__global__ void __launch_bounds__(32, EPI_FWD_MIN_BLOCKS6) ekf_forward_segmented_kernel(const __grid_constant__ EkfParams P) {
+  const int S = P.fwd_segments, T = P.T, k0 = P.k0;
+  const int n_tiles = (P.B + 31) / 32;
+  const int lane = threadIdx.x;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(P.fwd_sync, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_tiles * S) return;
+    const int seg = item / n_tiles, tile = item - seg * n_tiles;
+    // boundaries at or after k0: every resume page is on the (possibly lean) tape
+    const int kb = (seg == 0) ? 0 : k0 + (int)(((long long)(T - k0) * seg) / S);
+    const int ke = (seg + 1 == S) ? T : k0 + (int)(((long long)(T - k0) * (seg + 1)) / S);
+    if (seg > 0) {
+      if (lane == 0) {
+        while (atomicAdd(P.fwd_sync + 1 + tile, 0) < seg) __nanosleep(256);
+      }
+      __syncwarp();
+      __threadfence();
+    }
+    if (ke > kb || seg == 0) forward_days<MODEL, false, TILED>(P, tile * 32 + lane, kb, ke, nullptr);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(P.fwd_sync + 1 + tile, seg + 1);
+  }
 }
 
 template <int MODEL, bool TILED>
@@ -327,9 +395,55 @@ static void launch_fwd_model(const EkfParams &p, cudaStream_t st, bool monitor) 
   }
 }
 
+// Number of time segments for `tiles` one-warp CTAs on `slots` resident CTAs (1 = plain launch).
+// Measured on the 1844-tile sweep (B200, 1184 slots): the kernel saturates the SM from ~6 warps
+// per SM on, so segmenting only trims the idle tail of the last wave: S = 1 / 3 / 7 / 12 / 24 ->
+// 4.75 / 4.45 / 4.77 / 4.97 / 5.29 ms (each resume costs ~0.02 ms).  Three segments whenever the
+// batch is a few, non-integral waves.
+int forward_segments(long long tiles, int slots) {
+  if (tiles <= slots || tiles > 6LL * slots || tiles % slots == 0) return 1;
+  return 3;
+}
+
+template <int MODEL>
+static bool launch_fwd_segmented(const EkfParams &p, cudaStream_t st) {
+  if constexpr (model_dim(MODEL) == 6 && !model_legacy(MODEL)) {
+    static int slots = 0;
+    if (!slots) {
+      int dev = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_forward_segmented_kernel<MODEL, true>, 32, 0);
+      slots = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int tiles = (p.B + 31) / 32;
+    int grid = tiles < slots ? tiles : slots;
+    if (const char *e = getenv("EPI_FWD_GRID")) grid = atoi(e);  // tuning experiments
+    ekf_forward_segmented_kernel<MODEL, true><<<grid, 32, 0, st>>>(p);
+    return true;
+  } else {
+    return false;
+  }
+}
+
+int forward_resident_slots6() {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ekf_forward_segmented_kernel<EPI_MODEL_OPTCTRL, true>, 32, 0);
+  return sms * (per_sm > 0 ? per_sm : 1);
+}
+
 void launch_ekf_forward(const EkfParams &p, cudaStream_t st) {
   // the monitor is dead code unless rho is wanted or R adapts (beta != 1)
   const bool monitor = (p.rho.p != nullptr) || (p.beta != 1.0);
+  if (p.fwd_segments > 1 && p.fwd_sync && p.tiled && !monitor) {
+    bool done = false;
+#define CALL(MDL) done = launch_fwd_segmented<MDL>(p, st)
+    EPI_DISPATCH_MODEL(p.model, CALL)
+#undef CALL
+    if (done) return;
+  }
 #define CALL(MDL)                                                  \
   if (p.tiled) launch_fwd_model<MDL, true>(p, st, monitor);        \
   else launch_fwd_model<MDL, false>(p, st, monitor)

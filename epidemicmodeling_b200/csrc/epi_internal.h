@@ -50,6 +50,8 @@ struct EkfParams {
                                    //    models then hold the packed upper triangle (F = m(m+1)/2)
   int k0;                          // first day the smoother needs (0 = all).  Lean sweeps (tiled only):
                                    // the tape holds days k0..T-1, gains/backward run for k >= k0
+  int fwd_segments;                // > 1: time-segmented persistent forward launch (m = 6 generic, tiled, no monitor)
+  int *fwd_sync;                   //      [1 + tiles] ints, zeroed: item counter, per-tile finished segments
   TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1-k0][m*m][32]
   const double *dot_grp;           // per group [T]: input term of days without NaN inputs (NaN = per trajectory)
   const double *cost_grp;          // per group [T]: that day's sum_j w*u (sweep), or null
@@ -68,6 +70,8 @@ struct EkfParams {
 void launch_group_day(const epi_model_params *prm, const double *u, const double *weights, int n_groups,
                       int T, int L, double *dot_grp, double *cost_grp, cudaStream_t st);
 void launch_ekf_forward(const EkfParams &p, cudaStream_t st);
+int forward_segments(long long tiles, int slots);  // segment count minimising the idle tail (1 = plain launch)
+int forward_resident_slots6();                     // resident one-warp CTAs of the m = 6 forward kernel on this device
 void launch_eks_gain(const EkfParams &p, cudaStream_t st);
 void launch_eks_backward(const EkfParams &p, cudaStream_t st);
 

@@ -412,6 +412,25 @@ def test_sweep_lean_edge_shapes(engine, T_hist, T_fore):
         assert_bits(lean[k], full[k], f"lean {k} T_hist={T_hist} T_fore={T_fore}")
 
 
+@pytest.mark.parametrize("segments", [2, 5, 64])
+def test_sweep_segmented_forward_is_bit_identical(engine, segments, monkeypatch):
+    """The time-segmented persistent forward launch (few-wave batches) resumes from the tape pages
+    of the previous segment: same bits as the plain launch, full and lean, ragged last tile,
+    more segments than forecast days."""
+    inp, eps = cases.sweep_case(n_regions=3, n_eps=15, T_hist=33, T_fore=21)   # 45 trajectories: 2 tiles, one ragged
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    monkeypatch.setenv("EPI_FWD_SEGMENTS", "1")
+    ref = wl.run_sweep(engine, batch, eps, want_front=True, want_u_fore=True, want_P_first=True)
+    monkeypatch.setenv("EPI_FWD_SEGMENTS", str(segments))
+    seg = wl.run_sweep(engine, batch, eps, want_front=True, want_u_fore=True, want_P_first=True)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "P_first"):
+        assert_bits(seg[k], ref[k], f"segmented {k} S={segments}")
+    lean = wl.run_sweep(engine, batch, eps, want_front=True, want_u_fore=True, lean=True)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore"):
+        assert_bits(lean[k], ref[k], f"segmented lean {k} S={segments}")
+
+
 def test_sweep_with_noise_waves_and_device_mode(engine):
     import torch
     inp, eps = cases.sweep_case(n_regions=2, n_eps=9, T_hist=40, T_fore=20)
