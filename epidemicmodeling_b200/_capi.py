@@ -21,7 +21,7 @@ Q_CONST, Q_PERDAY_SCALAR, Q_PERDAY_FULL = 0, 1, 2
 R_CONST, R_PERDAY = 0, 1
 RATES_CONST, RATES_SHARED_SERIES, RATES_SERIES = 0, 1, 2
 SEIRP_OUT_FULL, SEIRP_OUT_FINAL = 0, 1
-U_F64, U_U8 = 0, 1
+U_F64, U_U8, U_PHILOX = 0, 1, 3
 
 _dp = C.c_void_p  # every array pointer is passed as a raw address (host or device)
 
@@ -47,7 +47,13 @@ class RolloutArgs(C.Structure):
     _fields_ = [("mem", C.c_int), ("B", C.c_int), ("K", C.c_int), ("L", C.c_int), ("G", C.c_int),
                 ("prm", _dp), ("x0", _dp), ("noise_std", _dp), ("u_kind", C.c_int), ("u", _dp),
                 ("noise", _dp), ("s", _dp), ("i", _dp), ("alpha", _dp), ("T_total", C.c_int),
-                ("j0_prefix", _dp), ("j1_prefix", _dp), ("w", _dp), ("J0", _dp), ("J1", _dp)]
+                ("j0_prefix", _dp), ("j1_prefix", _dp), ("w", _dp), ("J0", _dp), ("J1", _dp),
+                ("seed", C.c_ulonglong), ("first", C.c_longlong)]
+
+
+class SchedulesArgs(C.Structure):
+    _fields_ = [("mem", C.c_int), ("B", C.c_int), ("K", C.c_int), ("L", C.c_int), ("G", C.c_int),
+                ("prm", _dp), ("seed", C.c_ulonglong), ("first", C.c_longlong), ("u", _dp)]
 
 
 class NpiCostArgs(C.Structure):
@@ -102,6 +108,7 @@ SYMBOLS = {
     "epi_fp64_probe": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "epi_seirp_batch": (C.c_int, [C.c_void_p, C.POINTER(SeirpArgs)]),
     "epi_rollout_cost_batch": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs)]),
+    "epi_random_schedules": (C.c_int, [C.c_void_p, C.POINTER(SchedulesArgs)]),
     "epi_npicost_batch": (C.c_int, [C.c_void_p, C.POINTER(NpiCostArgs)]),
     "epi_si_controlled_batch": (C.c_int, [C.c_void_p, C.POINTER(SiArgs)]),
     "epi_ekf_eks_batch": (C.c_int, [C.c_void_p, C.POINTER(EkfArgs)]),

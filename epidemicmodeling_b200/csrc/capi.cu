@@ -423,21 +423,36 @@ extern "C" int epi_seirp_batch(epi_ctx *c, const epi_seirp_args *a) {
 // ---------------------------------------------------------------------------
 // SIalpha_Controlled + NPICost
 // ---------------------------------------------------------------------------
+// EPI_U_PHILOX draws integer levels lo..hi per NPI: both bounds must be integers in 0..255
+static void validate_levels_host(const epi_model_params *prm, long long n_groups, int L, const char *who) {
+  for (long long g = 0; g < n_groups; ++g)
+    for (int j = 0; j < L; ++j) {
+      const double lo = prm[g].u_min[j], hi = prm[g].u_max[j];
+      if (!(lo >= 0.0 && hi >= lo && hi <= 255.0) || lo != std::floor(lo) || hi != std::floor(hi))
+        bad_arg(std::string(who) + ": prm.u_min / prm.u_max must be integers with 0 <= u_min <= u_max <= 255");
+    }
+}
+
 extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
   return guarded(c, [&] {
     if (!a) bad_arg("null args");
     check_mem(a->mem);
     if (a->B < 0 || a->K < 0 || a->G < 1) bad_arg("epi_rollout_cost_batch: bad B/K/G");
     if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_rollout_cost_batch: L must be in 1..12");
-    if (a->u_kind != EPI_U_F64 && a->u_kind != EPI_U_U8) bad_arg("epi_rollout_cost_batch: bad u_kind");
+    if (a->u_kind != EPI_U_F64 && a->u_kind != EPI_U_U8 && a->u_kind != EPI_U_PHILOX)
+      bad_arg("epi_rollout_cost_batch: bad u_kind");
+    const bool gen = a->u_kind == EPI_U_PHILOX;
+    if (gen && (a->first < 0 || a->first % a->G != 0))
+      bad_arg("epi_rollout_cost_batch: first must be a non-negative multiple of G");
     if ((a->J0 == nullptr) != (a->J1 == nullptr)) bad_arg("epi_rollout_cost_batch: J0 and J1 go together");
     if (a->B == 0) return;
-    if (!a->prm || !a->x0 || (a->K > 0 && !a->u)) bad_arg("epi_rollout_cost_batch: prm, x0 and u are required");
+    if (!a->prm || !a->x0 || (a->K > 0 && !a->u && !gen)) bad_arg("epi_rollout_cost_batch: prm, x0 and u are required");
     if (a->J0 && a->T_total < 1) bad_arg("epi_rollout_cost_batch: T_total must be >= 1 when costs are requested");
     reset_phases(c);
     const long long B = a->B;
     const int K = a->K, L = a->L;
     const long long n_groups = (B + a->G - 1) / a->G;
+    if (gen && a->mem == EPI_MEM_HOST) validate_levels_host(a->prm, n_groups, L, "epi_rollout_cost_batch");
     Call shared(c, a->mem);
     const epi_model_params *prm = shared.in(a->prm, (size_t)n_groups);
     const double *x0 = shared.in(a->x0, (size_t)3 * n_groups);
@@ -445,7 +460,7 @@ extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
     const double *j0p = shared.in(a->j0_prefix, (size_t)n_groups);
     const double *j1p = shared.in(a->j1_prefix, (size_t)n_groups);
     const double *wts = shared.in(a->w, (size_t)n_groups * K * L);
-    const size_t usz = a->u_kind == EPI_U_F64 ? 8 : 1;
+    const size_t usz = a->u_kind == EPI_U_F64 ? 8 : gen ? 0 : 1;
     size_t per = (size_t)K * L * usz + (a->noise ? (size_t)K * 24 : 0) +
                  ((a->s ? 1 : 0) + (a->i ? 1 : 0) + (a->alpha ? 1 : 0)) * (size_t)K * 8 + 16;
     const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, per, scratch_budget(c)) : B;
@@ -456,7 +471,11 @@ extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
       p.B = (int)nb; p.K = K; p.L = L; p.G = a->G; p.b0 = b0;
       p.prm = prm; p.x0 = x0; p.noise_std = nstd;
       p.u_kind = a->u_kind;
-      if (a->u_kind == EPI_U_F64)
+      p.seed = a->seed;
+      p.first = a->first;
+      if (gen) {
+        // nothing to stage: the kernel draws the schedule from (seed, first + b0 + b)
+      } else if (a->u_kind == EPI_U_F64)
         p.u = w.traj_in_raw<double>((const double *)a->u, (size_t)K * L, B, b0, nb, &p.u_stride, &p.u_off);
       else
         p.u = w.traj_in_raw<unsigned char>((const unsigned char *)a->u, (size_t)K * L, B, b0, nb, &p.u_stride, &p.u_off);
@@ -474,6 +493,31 @@ extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
       ph.end();
       w.flush();
     }
+    finish(c, a->mem);
+  });
+}
+
+extern "C" int epi_random_schedules(epi_ctx *c, const epi_schedules_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->K < 0 || a->G < 1) bad_arg("epi_random_schedules: bad B/K/G");
+    if (a->L < 1 || a->L > EPI_LMAX) bad_arg("epi_random_schedules: L must be in 1..12");
+    if (a->first < 0 || a->first % a->G != 0) bad_arg("epi_random_schedules: first must be a non-negative multiple of G");
+    if (a->B == 0 || a->K == 0) return;
+    if (!a->prm || !a->u) bad_arg("epi_random_schedules: prm and u are required");
+    reset_phases(c);
+    const long long B = a->B;
+    const long long n_groups = (B + a->G - 1) / a->G;
+    if (a->mem == EPI_MEM_HOST) validate_levels_host(a->prm, n_groups, a->L, "epi_random_schedules");
+    Call shared(c, a->mem);
+    const epi_model_params *prm = shared.in(a->prm, (size_t)n_groups);
+    unsigned char *u = shared.out(a->u, (size_t)a->K * a->L * B);
+    PhaseScope ph(c, "random_schedules");
+    launch_random_schedules(prm, a->seed, a->first, (int)B, a->K, a->L, a->G, u, B, 0, c->stream);
+    check_launch(c, 1);
+    ph.end();
+    shared.flush();
     finish(c, a->mem);
   });
 }

@@ -384,6 +384,29 @@ EPI_DI double mul_X_At_ij(const XMat &X, const Mat<M, false> &A, int i, int j) {
   return acc;
 }
 
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3",
+// SC'11): ten rounds of two 32x32->64 multiplies and a key schedule.
+struct Philox4 { unsigned v[4]; };
+EPI_DI Philox4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+// the random-schedule rule of include/epi_b200.h (EPI_U_PHILOX): levels of NPIs 4q..4q+3 on `day`
+// for 0-based scenario `sc` of `region`; held scenarios (2*(sc+1) < G) use day 0
+EPI_DI bool schedule_held(long long sc, int G) { return 2 * (sc + 1) < (long long)G; }
+EPI_DI unsigned level_from_word(unsigned word, int lo, int hi) {
+  return (unsigned)lo + __umulhi(word, (unsigned)(hi - lo + 1));
+}
+
 // spacing of doubles at |x| (MATLAB eps(x)), normal x
 EPI_DI double eps_of(double x) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(fabs(x));

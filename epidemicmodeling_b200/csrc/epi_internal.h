@@ -90,7 +90,9 @@ struct RolloutParams {
   long long b0;
   const epi_model_params *prm;
   const double *x0, *noise_std;   // per group [3]
-  int u_kind;  // EPI_U_F64, EPI_U_U8, or 2 = precomputed per-day scalars (sweep)
+  int u_kind;  // EPI_U_F64, EPI_U_U8, 2 = precomputed per-day scalars (sweep), EPI_U_PHILOX = generated
+  unsigned long long seed;        // EPI_U_PHILOX
+  long long first;                // EPI_U_PHILOX: global index of the caller's trajectory 0
   const void *u; long long u_stride, u_off;   // [K][L][B]
   CArr noise;                     // [K][3][B]
   TArr s, i, alpha;               // [K][B]
@@ -102,6 +104,9 @@ struct RolloutParams {
   TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);
+// write the EPI_U_PHILOX schedules: u [K][L][stride] uint8, trajectories first + b0 + (0..B-1)
+void launch_random_schedules(const epi_model_params *prm, unsigned long long seed, long long first, int B, int K,
+                             int L, int G, unsigned char *u, long long stride, long long off, cudaStream_t st);
 
 struct SiParams {
   int B, K;

@@ -192,7 +192,12 @@ void launch_seirp(const SeirpParams &p, cudaStream_t st) {
 // SIalpha_Controlled (Tools/SIalpha_Controlled.m:15-32) fused with NPICost
 // (Tools/NPICost.m:6-10) as chained in TrainPredictPrescribeNPI.m:481-493,512-519
 // ===========================================================================
-// U_KIND: EPI_U_F64, EPI_U_U8, 2 = per-day scalars precomputed by eks_backward
+// exact integer -> double without the multi-instruction I2F sequence: 2^52 + v has v in its
+// low mantissa bits, so (2^52 + v) - 2^52 == v exactly for 0 <= v < 2^32
+EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+
+// U_KIND: EPI_U_F64, EPI_U_U8, 2 = per-day scalars precomputed by eks_backward,
+// EPI_U_PHILOX = schedules generated in registers (no HBM stream at all)
 template <int U_KIND>
 __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,6 +236,12 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   }
   const int Th = (U_KIND == 2) ? P.T_hist : 0;
   const size_t us = (size_t)P.u_stride, ns = (size_t)P.noise.stride;
+  // EPI_U_PHILOX: this trajectory is scenario sc of region rg (include/epi_b200.h)
+  const long long gidx = P.first + P.b0 + b;
+  const unsigned rg = (unsigned)(gidx / P.G), sc = (unsigned)(gidx % P.G);
+  const bool held = schedule_held((long long)sc, P.G);
+  const unsigned key0 = (unsigned)P.seed, key1 = (unsigned)(P.seed >> 32);
+  unsigned lvl[EPI_LMAX];
   const double *__restrict__ nz = P.noise.p ? P.noise.p + P.noise.off + b : nullptr;
   for (int t = 0; t < K; ++t) {  // :24-28
     double dot, cday = 0.0;
@@ -240,12 +251,25 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     } else {
       dot = 0.0;
       const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
+      if (U_KIND == EPI_U_PHILOX && (t == 0 || !held)) {
+#pragma unroll
+        for (int q = 0; q < EPI_LMAX / 4; ++q) {
+          if (4 * q < L) {
+            const Philox4 w4 = philox4x32_10(held ? 0u : (unsigned)t, (unsigned)q, sc, rg, key0, key1);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (4 * q + r < L)
+                lvl[4 * q + r] = level_from_word(w4.v[r], (int)prm->u_min[4 * q + r], (int)prm->u_max[4 * q + r]);
+          }
+        }
+      }
 #pragma unroll
       for (int j = 0; j < EPI_LMAX; ++j) {
         if (j < L) {
           double uj;
           const size_t ui = ((size_t)t * L + j) * us + (size_t)P.u_off + b;
           if (U_KIND == EPI_U_F64) uj = ((const double *)P.u)[ui];
+          else if (U_KIND == EPI_U_PHILOX) uj = u32_to_double(lvl[j]);
           else uj = (double)((const unsigned char *)P.u)[ui];
           const double gj = gamma * prm->a[j];
           const double d = prm->u_max[j] - uj;
@@ -318,9 +342,6 @@ EPI_DI void bulk_load_row(void *sdst, const void *gsrc, unsigned bytes, unsigned
       : "memory");
 }
 
-// exact integer -> double without the multi-instruction I2F sequence: 2^52 + v has v in its
-// low mantissa bits, so (2^52 + v) - 2^52 == v exactly for 0 <= v < 2^32
-EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
 EPI_DI double stage_value(const unsigned char *p) { return u32_to_double((unsigned)*p); }
 EPI_DI double stage_value(const double *p) { return *p; }
 
@@ -491,6 +512,39 @@ static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
   return true;
 }
 
+// the EPI_U_PHILOX schedules written out: one thread per (trajectory, group of 4 NPIs), days in a loop
+__global__ void __launch_bounds__(256) random_schedules_kernel(const epi_model_params *__restrict__ prm,
+                                                               unsigned long long seed, long long first, int B, int K,
+                                                               int L, int G, unsigned char *__restrict__ u,
+                                                               long long stride, long long off) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nq = (L + 3) / 4;
+  if (tid >= (long long)B * nq) return;
+  const int q = (int)(tid / B), b = (int)(tid % B);  // b fastest: coalesced byte stores
+  const long long gidx = first + b;
+  const unsigned rg = (unsigned)(gidx / G), sc = (unsigned)(gidx % G);
+  const bool held = schedule_held((long long)sc, G);
+  const epi_model_params *__restrict__ pm = prm + b / G;  // tables are local to the call, counters global
+  unsigned lv[4] = {0, 0, 0, 0};
+  for (int t = 0; t < K; ++t) {
+    if (t == 0 || !held) {
+      const Philox4 w4 = philox4x32_10(held ? 0u : (unsigned)t, (unsigned)q, sc, rg, (unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (4 * q + r < L) lv[r] = level_from_word(w4.v[r], (int)pm->u_min[4 * q + r], (int)pm->u_max[4 * q + r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (4 * q + r < L) u[((size_t)t * L + 4 * q + r) * (size_t)stride + (size_t)off + b] = (unsigned char)lv[r];
+  }
+}
+void launch_random_schedules(const epi_model_params *prm, unsigned long long seed, long long first, int B, int K,
+                             int L, int G, unsigned char *u, long long stride, long long off, cudaStream_t st) {
+  const long long total = (long long)B * ((L + 3) / 4);
+  if (total <= 0 || K <= 0) return;
+  random_schedules_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(prm, seed, first, B, K, L, G, u, stride, off);
+}
+
 void launch_rollout(const RolloutParams &p, cudaStream_t st) {
   if (p.u_kind == EPI_U_F64 && rollout_launch_staged<EPI_U_F64>(p, st)) return;
   if (p.u_kind == EPI_U_U8 && rollout_launch_staged<EPI_U_U8>(p, st)) return;
@@ -498,6 +552,7 @@ void launch_rollout(const RolloutParams &p, cudaStream_t st) {
   const int grid = (p.B + block - 1) / block;
   if (p.u_kind == EPI_U_F64) rollout_kernel<EPI_U_F64><<<grid, block, 0, st>>>(p);
   else if (p.u_kind == EPI_U_U8) rollout_kernel<EPI_U_U8><<<grid, block, 0, st>>>(p);
+  else if (p.u_kind == EPI_U_PHILOX) rollout_kernel<EPI_U_PHILOX><<<grid, block, 0, st>>>(p);
   else rollout_kernel<2><<<grid, block, 0, st>>>(p);
 }
 

@@ -220,9 +220,14 @@ class Engine:
     # -- rollout + cost ---------------------------------------------------------
     def rollout_cost(self, prm, x0, u, K_, L, G=1, B=None, noise_std=None, noise=None,
                      want_traj=True, want_cost=False, T_total=None, j0_prefix=None,
-                     j1_prefix=None, w=None):
-        """Tools/SIalpha_Controlled.m (+ Tools/NPICost.m fused).  u [K,L,B] float64 or uint8."""
+                     j1_prefix=None, w=None, seed=None, first=0):
+        """Tools/SIalpha_Controlled.m (+ Tools/NPICost.m fused).  u [K,L,B] float64 or uint8, or
+        u=None with `seed`: the random schedules of TrainPredictPrescribeNPI.m:499-510 are
+        generated in the kernel (EPI_U_PHILOX; `first` = global index of trajectory 0)."""
         mem = self._mode(x0, u, noise)
+        if u is None:
+            if seed is None or B is None:
+                raise ValueError("generated schedules need seed= and B=")
         if B is None:
             B = int(u.shape[-1])
         a = K.RolloutArgs()
@@ -231,9 +236,12 @@ class Engine:
         a.prm = self._prm(prm, mem)
         a.x0 = self._in(x0, mem, n=3 * ng)
         a.noise_std = self._in(noise_std, mem, n=3 * ng)
-        is_u8 = (u.dtype == np.uint8) if not _is_torch(u) else (u.dtype == torch.uint8)
-        a.u_kind = K.U_U8 if is_u8 else K.U_F64
-        a.u = self._in(u, mem, dtype=np.uint8 if is_u8 else np.float64, n=K_ * L * B)
+        if u is None:
+            a.u_kind, a.seed, a.first = K.U_PHILOX, int(seed), int(first)
+        else:
+            is_u8 = (u.dtype == np.uint8) if not _is_torch(u) else (u.dtype == torch.uint8)
+            a.u_kind = K.U_U8 if is_u8 else K.U_F64
+            a.u = self._in(u, mem, dtype=np.uint8 if is_u8 else np.float64, n=K_ * L * B)
         a.noise = self._in(noise, mem, n=K_ * 3 * B)
         res = {}
         if want_traj:
@@ -252,6 +260,20 @@ class Engine:
         finally:
             self._done()
         return res
+
+    def random_schedules(self, prm, B, K_, L, G, seed, first=0, device=False):
+        """The schedules EPI_U_PHILOX integrates, written out: uint8 [K,L,B]."""
+        mem = K.MEM_DEVICE if device else K.MEM_HOST
+        a = K.SchedulesArgs()
+        a.mem, a.B, a.K, a.L, a.G = mem, int(B), int(K_), int(L), int(G)
+        a.prm = self._prm(prm, mem)
+        a.seed, a.first = int(seed), int(first)
+        u, a.u = self._out((K_, L, B), mem, dtype=np.uint8)
+        try:
+            self._ck(self._lib.epi_random_schedules(self._h, C.byref(a)))
+        finally:
+            self._done()
+        return u
 
     def npicost(self, newcases, inputs, weights, T, L, G=1):
         """Tools/NPICost.m: newcases [T,B], inputs [T,L,B], weights per group [T,L]."""

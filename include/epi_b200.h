@@ -136,7 +136,15 @@ int epi_seirp_batch(epi_ctx *ctx, const epi_seirp_args *a);
  *      and  [J0,J1] = NPICost(newcases, inputs, weights)       Tools/NPICost.m:1
  *      as chained in Tools/TrainPredictPrescribeNPI.m:481-493,512-519.
  * The reference's in-line randn draws become the explicit `noise` input. */
-enum { EPI_U_F64 = 0, EPI_U_U8 = 1 };
+enum { EPI_U_F64 = 0, EPI_U_U8 = 1, EPI_U_PHILOX = 3 };
+/* EPI_U_PHILOX: the schedules are not supplied but generated in the kernel with the rule of
+ * Tools/TrainPredictPrescribeNPI.m:499-510 -- trajectory b of a group is Monte-Carlo scenario
+ * sc = (b mod G) + 1 of region b / G; scenarios with sc < G/2 draw ONE level per NPI and hold it
+ * over time, the others draw one level per NPI per day; every draw is uniform on the integers
+ * [prm.u_min(j), prm.u_max(j)] (MATLAB randi).  The reference's global Mersenne-Twister stream
+ * becomes a counter-based one: word (j mod 4) of Philox4x32-10(counter = {day, j / 4, sc - 1,
+ * region}, key = seed), day = 0 for the held scenarios, mapped to a level by
+ * lo + floor(word * (hi - lo + 1) / 2^32).  Same schedule on any GPU count and wave split. */
 typedef struct {
   int mem;
   int B, K, L, G;
@@ -153,8 +161,22 @@ typedef struct {
   const double *j1_prefix;     /* per group: sum of weights.*inputs over the history */
   const double *w;             /* per group [K][L]: day-wise weights of the forecast block */
   double *J0, *J1;             /* [B] */
+  unsigned long long seed;     /* EPI_U_PHILOX: the Philox key (u is ignored) */
+  long long first;             /* EPI_U_PHILOX: global index of trajectory 0 of this call (sharded batches) */
 } epi_rollout_args;
 int epi_rollout_cost_batch(epi_ctx *ctx, const epi_rollout_args *a);
+
+/* The schedules EPI_U_PHILOX integrates, written out: u [K][L][B] uint8 (e.g. to recover the
+ * schedule of the Pareto knee).  Same (seed, first, G, prm) as the rollout call. */
+typedef struct {
+  int mem;
+  int B, K, L, G;
+  const epi_model_params *prm; /* per group: u_min, u_max */
+  unsigned long long seed;
+  long long first;
+  unsigned char *u;            /* [K][L][B] */
+} epi_schedules_args;
+int epi_random_schedules(epi_ctx *ctx, const epi_schedules_args *a);
 
 /* replaces  [J0,J1] = NPICost(newcases, inputs, weights)          Tools/NPICost.m:1
  * as a stand-alone call (the rollout above fuses it).  newcases [T][B],

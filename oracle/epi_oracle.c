@@ -161,6 +161,41 @@ void orc_pareto(const double *J0, const double *J1, int n, unsigned char *on_fro
 }
 
 /* ------------------------------------------------------------------------- */
+/* random NPI schedules: TrainPredictPrescribeNPI.m:499-510 on a counter-based stream */
+/* ------------------------------------------------------------------------- */
+/* Philox4x32-10 (Salmon et al., SC'11).  Third-party algorithm, restated from the paper:
+ * round: (hi0,lo0) = M0*c0, (hi1,lo1) = M1*c2; c = {hi1^c1^k0, lo1, hi0^c3^k1, lo0};
+ * key += (W0, W1) after every round; 10 rounds. */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* Schedule of Monte-Carlo scenario `scenario` (0-based) of `region`, n_scenarios per region:
+ * scenarios with (scenario+1) < n_scenarios/2 hold one randi([u_min(j), u_max(j)]) per NPI over
+ * all K days (:502-503), the others draw per NPI per day (:505-507).  Draw (j, day) =
+ * word (j mod 4) of Philox(counter {day, j/4, scenario, region}, key seed), day = 0 when held;
+ * level = lo + floor(word*(hi-lo+1)/2^32).  u [K][L] uint8. */
+void orc_random_schedule(uint64_t seed, uint32_t region, uint32_t scenario, int n_scenarios, int L, int K,
+                         const double *u_min, const double *u_max, unsigned char *u) {
+  const int held = 2 * ((long long)scenario + 1) < (long long)n_scenarios;
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int t = 0; t < K; ++t)
+    for (int j = 0; j < L; ++j) {
+      const uint32_t ctr[4] = {held ? 0u : (uint32_t)t, (uint32_t)(j / 4), scenario, region};
+      uint32_t w[4];
+      orc_philox4x32_10(ctr, key, w);
+      const int lo = (int)u_min[j], hi = (int)u_max[j];
+      u[t * L + j] = (unsigned char)(lo + (int)(((uint64_t)w[j & 3] * (uint64_t)(hi - lo + 1)) >> 32));
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* pinv / mrdivide as DEFINED by the oracle                                  */
 /* ------------------------------------------------------------------------- */
 

@@ -33,6 +33,7 @@
  */
 #ifndef EPI_ORACLE_H
 #define EPI_ORACLE_H
+#include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -102,6 +103,11 @@ void orc_npicost(const double *newcases, int T, const double *inputs, const doub
 /* Tools/TrainPredictPrescribeNPI.m:624-633: strict-dominance Pareto mask and
  * knee index (0-based; first minimum, NaN skipped as MATLAB's min does). */
 void orc_pareto(const double *J0, const double *J1, int n, unsigned char *on_front, int *I_opt);
+
+/* random NPI schedules (TrainPredictPrescribeNPI.m:499-510) on a Philox4x32-10 counter stream */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void orc_random_schedule(uint64_t seed, uint32_t region, uint32_t scenario, int n_scenarios, int L, int K,
+                         const double *u_min, const double *u_max, unsigned char *u);
 
 /* pinv as DEFINED by this oracle for the generic smoother
  * (Tools/GenericExtendedKalmanFilter.m:215).  A, X are mxm column-major

@@ -168,6 +168,24 @@ def NPICost(newcases, inputs, weights):
     return J0.value, J1.value
 
 
+def philox4x32_10(ctr, key):
+    """Philox4x32-10 block: ctr (4 uint32), key (2 uint32) -> 4 uint32."""
+    c = (C.c_uint32 * 4)(*[int(v) & 0xFFFFFFFF for v in ctr])
+    k = (C.c_uint32 * 2)(*[int(v) & 0xFFFFFFFF for v in key])
+    o = (C.c_uint32 * 4)()
+    lib().orc_philox4x32_10(c, k, o)
+    return [int(v) for v in o]
+
+
+def random_schedule(seed, region, scenario, n_scenarios, L, K, u_min, u_max):
+    """TrainPredictPrescribeNPI.m:499-510 on the Philox stream: uint8 [L, K] (MATLAB shape)."""
+    u = np.zeros((K, L), dtype=np.uint8)
+    lib().orc_random_schedule(C.c_uint64(int(seed)), C.c_uint32(int(region)), C.c_uint32(int(scenario)),
+                              C.c_int(int(n_scenarios)), C.c_int(int(L)), C.c_int(int(K)),
+                              _p(_f(u_min)), _p(_f(u_max)), u.ctypes.data_as(C.c_void_p))
+    return u.T.copy()
+
+
 def pareto(J0, J1):
     J0, J1 = _f(J0).ravel(), _f(J1).ravel()
     n = J0.size

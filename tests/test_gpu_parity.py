@@ -360,6 +360,43 @@ def test_ekf6_per_trajectory_epsilon_batch(engine):
     assert out["status"].shape == (eps.size,)
 
 
+@pytest.mark.parametrize("nS", [10, 257])
+def test_generated_schedules_match_oracle_and_supplied(engine, nS):
+    """EPI_U_PHILOX: the schedules drawn in the kernel are the oracle's (bit for bit), integrating
+    them equals integrating the same schedules supplied as uint8, and a batch split at a region
+    boundary (`first`) reproduces the unsplit result."""
+    nR, Kn, L = 3, 37, 12
+    reg = syn.load_regions(nR)
+    B = nR * nS
+    umin = np.zeros(L)
+    prm_d = [dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                  u_min=umin, alpha_min=1e-8, alpha_max=100.0) for r in range(nR)]
+    prm = pack_params(prm_d, L)
+    x0 = np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)])
+    w = np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)])
+    seed = 0x1234_5678_9ABC_DEF0
+    u = engine.random_schedules(prm, B, Kn, L, nS, seed)
+    assert u.dtype == np.uint8 and u.shape == (Kn, L, B)
+    o = orc()
+    for b in sorted(set(list(range(0, B, 41)) + [nS // 2 - 2, nS // 2 - 1, nS // 2, B - 1])):
+        ref = o.random_schedule(seed, b // nS, b % nS, nS, L, Kn, umin, reg["npi_max"])
+        assert np.array_equal(u[:, :, b].T, ref), f"schedule of trajectory {b}"
+    kw = dict(G=nS, want_traj=True, want_cost=True, T_total=Kn, w=w)
+    gen = engine.rollout_cost(prm, x0, None, Kn, L, B=B, seed=seed, **kw)
+    sup = engine.rollout_cost(prm, x0, u, Kn, L, **kw)
+    for k in ("s", "i", "alpha", "J0", "J1"):
+        assert_bits(gen[k], sup[k], f"generated vs supplied {k}")
+    # shard: regions 1.. as their own call
+    tail = engine.rollout_cost(pack_params(prm_d[1:], L), x0[1:], None, Kn, L, B=B - nS, seed=seed, first=nS,
+                               G=nS, want_traj=False, want_cost=True, T_total=Kn, w=w[1:])
+    assert_bits(tail["J0"], gen["J0"][nS:]); assert_bits(tail["J1"], gen["J1"][nS:])
+    with pytest.raises(K.EpiError):
+        engine.rollout_cost(prm, x0, None, Kn, L, B=B, seed=seed, first=1, **kw)   # not a multiple of G
+    bad = pack_params([dict(d, u_min=np.full(L, np.nan)) for d in prm_d], L)
+    with pytest.raises(K.EpiError):
+        engine.rollout_cost(bad, x0, None, Kn, L, B=B, seed=seed, **kw)            # level bounds are required
+
+
 # ------------------------------------------------------------------------------ fused sweep
 def _run_sweep(engine, inp, eps, **kw):
     S = wl.run_fixed_input(engine, inp)

@@ -307,3 +307,42 @@ def test_pinv_sensitivity_is_reported_not_hidden(capsys):
     with capsys.disabled():
         print(f"\n[pinv sensitivity] bang-bang entries differing Jacobi-pinv vs SVD-pinv: {flips}/{total}")
     assert flips <= total
+
+
+# ---------------------------------------------------------------------------- random schedules
+def test_philox4x32_10_known_answers():
+    """Random123's published known-answer vectors (kat_vectors: philox4x32 10 rounds)."""
+    assert orc.philox4x32_10([0] * 4, [0] * 2) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert orc.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert orc.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_random_schedule_rule():
+    """TrainPredictPrescribeNPI.m:499-510: scenario < n/2 (1-based) holds one randi per NPI over
+    time, the others draw per NPI per day; levels are integers in [NPI_MINS, NPI_MAXES]."""
+    umax = np.array([3, 3, 2, 4, 2, 3, 2, 4, 2, 3, 2, 4.0])
+    umin = np.zeros(12)
+    n, K = 500, 120
+    for sc in (0, 100, 248):                       # 1-based 1, 101, 249 < 250
+        u = orc.random_schedule(5, 3, sc, n, 12, K, umin, umax)
+        assert u.shape == (12, K) and (u == u[:, :1]).all()
+    for sc in (249, 250, 499):                     # 1-based 250.. are per-day
+        u = orc.random_schedule(5, 3, sc, n, 12, K, umin, umax)
+        assert not (u == u[:, :1]).all()
+        assert (u <= umax[:, None]).all()
+        for j in range(12):                        # every level of every NPI occurs
+            assert set(np.unique(u[j])) == set(range(int(umax[j]) + 1))
+    # a shifted minimum shifts the support, and streams differ by region / scenario / seed
+    u1 = orc.random_schedule(5, 3, 300, n, 12, K, umin + 1, umax + 1)
+    assert u1.min() >= 1 and np.array_equal(u1, orc.random_schedule(5, 3, 300, n, 12, K, umin, umax) + 1)
+    base = orc.random_schedule(5, 3, 300, n, 12, K, umin, umax)
+    for other in (orc.random_schedule(6, 3, 300, n, 12, K, umin, umax),
+                  orc.random_schedule(5, 4, 300, n, 12, K, umin, umax),
+                  orc.random_schedule(5, 3, 301, n, 12, K, umin, umax)):
+        assert not np.array_equal(base, other)
+    # level frequencies are uniform (chi-square, 3 degrees of freedom for NPI 0 over 40 scenarios)
+    lv = np.concatenate([orc.random_schedule(5, 0, sc, n, 12, K, umin, umax)[0] for sc in range(250, 290)])
+    cnt = np.bincount(lv, minlength=4)
+    chi2 = ((cnt - lv.size / 4) ** 2 / (lv.size / 4)).sum()
+    assert chi2 < 16.3                              # p = 0.001

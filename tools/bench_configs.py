@@ -135,7 +135,7 @@ def main():
             u8[:, j, :] = torch.where(first_half[None, :], const.expand(Kn, Bm), per_day)
             del per_day, const
         prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
-                                alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
+                                u_min=np.zeros(L), alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
         x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)]))
         w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)]))
         j0p, j1p = torch.zeros(nR, dtype=torch.float64, device=dev), torch.zeros(nR, dtype=torch.float64, device=dev)
@@ -150,6 +150,27 @@ def main():
         out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
                     "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
                     "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
+
+        # the same scoring with the schedules drawn in the kernel (Philox, seed 5: SURVEY 8d config 5,
+        # no HBM stream at all) -- and the supplied-u8 path fed with exactly those schedules must agree
+        del u8
+        torch.cuda.empty_cache()
+
+        def run5g():
+            holder["g"] = eng.rollout_cost(prmd, x0, None, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
+                                           T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w, seed=5)
+        timed(run5g, reps=3, warm=1)
+        ms = sum(eng.last_kernel_times().values())
+        ug = eng.random_schedules(prmd, Bm, Kn, L, nS, 5, device=True)
+        chk = eng.rollout_cost(prmd, x0, ug, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True, T_total=Kn,
+                               j0_prefix=j0p, j1_prefix=j1p, w=w)
+        eng.sync()
+        same = bool(torch.equal(chk["J0"], holder["g"]["J0"]) and torch.equal(chk["J1"], holder["g"]["J1"]))
+        out.append({"config": 5, "kernel": "rollout_cost[philox, generated in-kernel]", "B": Bm, "K": Kn, "ms": ms,
+                    "trajectory_days_per_s": units / ms * 1e3, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64,
+                    "bit_identical_to_supplied_u8": same})
+        del ug, chk
+        holder["o"] = holder["g"]
 
         J0, J1 = holder["o"]["J0"].view(nR, nS), holder["o"]["J1"].view(nR, nS)
         ms = timed(lambda: holder.__setitem__("p", eng.pareto(J0, J1)), reps=3, warm=1)
