@@ -19,7 +19,7 @@ ROUND_ROBIN = [[(0, 1), (2, 3), (4, 5)], [(0, 2), (1, 4), (3, 5)], [(0, 4), (1, 
                [(0, 3), (1, 5), (2, 4)], [(0, 5), (1, 2), (3, 4)]]
 
 
-def jacobi_stats(A, sets, warp=32):
+def jacobi_stats(A, sets, warp=32, local=None):
     """A [N,6,6] symmetric.  Vectorised threshold Jacobi.  Returns per-matrix rotations, sweeps,
     and warp-level executed set count (a set executes for a warp if any lane rotates any pair)."""
     a = A.copy()
@@ -35,7 +35,13 @@ def jacobi_stats(A, sets, warp=32):
         dmax = np.abs(np.einsum("nii->ni", a)).max(1)
         thr = dmax * REL
         off = np.abs(a[:, iu[0], iu[1]]).max(1)
-        alive &= off > thr
+        if local is None:
+            alive &= off > thr
+        else:
+            d = np.abs(np.einsum("nii->ni", a))
+            with np.errstate(all="ignore"):
+                crit = (a[:, iu[0], iu[1]] ** 2) > local * d[:, iu[0]] * d[:, iu[1]]
+            alive &= crit.any(1)
         if not alive.any():
             break
         sweeps[alive] += 1
@@ -45,7 +51,11 @@ def jacobi_stats(A, sets, warp=32):
             act_set = np.zeros(N, bool)
             for (p, q) in st:
                 apq = a[:, p, q]
-                act = alive & (np.abs(apq) > thr)
+                if local is None:
+                    act = alive & (np.abs(apq) > thr)
+                else:
+                    with np.errstate(all="ignore"):
+                        act = alive & (apq * apq > local * np.abs(a[:, p, p] * a[:, q, q]))
                 act_set |= act
                 if not act.any():
                     continue
@@ -70,7 +80,7 @@ def jacobi_stats(A, sets, warp=32):
                 rot[idx] += 1
             wa = np.zeros(nw * warp, bool); wa[:N] = act_set
             warp_sets += wa.reshape(nw, warp).any(1)
-    return rot, sweeps, warp_sets, warp_sweeps
+    return rot, sweeps, warp_sets, warp_sweeps, a
 
 
 def main():
@@ -90,10 +100,17 @@ def main():
                 mats.append(np.transpose(out["P_MINUS"], (2, 0, 1))[1:])  # [T-1,6,6]
             # warp = 32 eps of one day: order matrices day-major, eps-minor
             A = np.stack(mats, 1).reshape(-1, 6, 6)
-            for name, sets in (("row-cyclic", ROW_CYCLIC), ("round-robin", ROUND_ROBIN)):
-                rot, sw, wsets, wsw = jacobi_stats(A, sets)
-                print(f"region {r} eps[{e0}:{e0+32}] {name:12s} rot/matrix {rot.mean():6.2f} (max {rot.max()}) "
-                      f"sweeps {sw.mean():5.2f} (max {sw.max()})  warp: sets {wsets.mean():6.2f} sweeps {wsw.mean():5.2f}")
+            for name, sets, local in (("round-robin", ROUND_ROBIN, None), ("rr local 2^-106", ROUND_ROBIN, 2.0 ** -106),
+                                      ("rr local 2^-100", ROUND_ROBIN, 2.0 ** -100)):
+                rot, sw, wsets, wsw, ad = jacobi_stats(A, sets, local=local)
+                lam = np.sort(np.abs(np.einsum("nii->ni", ad)), 1)
+                if local is None:
+                    lam_ref = lam
+                with np.errstate(all="ignore"):
+                    rel = np.nanmax(np.abs(lam - lam_ref) / np.maximum(lam_ref, 1e-300), axis=1)
+                print(f"region {r} eps[{e0}:{e0+32}] {name:16s} rot/matrix {rot.mean():6.2f} (max {rot.max()}) "
+                      f"sweeps {sw.mean():5.2f} (max {sw.max()})  warp: sets {wsets.mean():6.2f} sweeps {wsw.mean():5.2f} "
+                      f"| eig rel diff vs global: median {np.median(rel):.1e} max {rel.max():.1e}")
 
 
 if __name__ == "__main__":
