@@ -112,9 +112,10 @@ EPI_DI TrajIn traj_inputs(const EkfParams &P, int b, int M) {
   return t;
 }
 EPI_DI double q_elem(const double *__restrict__ Q, int q_mode, int M, int k, int i, int j) {
-  if (q_mode == EPI_Q_CONST) return Q[j * M + i];
-  if (q_mode == EPI_Q_PERDAY_FULL) return Q[(size_t)k * M * M + j * M + i];
-  return (i == j) ? Q[k] : 0.0;  // B*q*B' with B = I
+  // read-only path: the loads may then be scheduled across the tape stores of the same day
+  if (q_mode == EPI_Q_CONST) return __ldg(Q + j * M + i);
+  if (q_mode == EPI_Q_PERDAY_FULL) return __ldg(Q + (size_t)k * M * M + j * M + i);
+  return (i == j) ? __ldg(Q + k) : 0.0;  // B*q*B' with B = I
 }
 
 #define EPI_DISPATCH_MODEL(model, CALL)                                   \

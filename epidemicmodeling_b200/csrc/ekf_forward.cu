@@ -125,8 +125,19 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
   double R_over = 0.0;        // adapted R for the next step (:184)
   bool has_over = false;
 
+  // the three per-day scalars (observation, R, per-group input term) are fetched one day ahead:
+  // they come from L2/HBM (each is read once) and were the exposed latency of every step
+  auto day_x = [&](int kk) { return __ldg(in.x + (size_t)(REV ? (T - 1 - kk) : kk) * in.x_ts); };
+  auto day_R = [&](int kk) { return (P.r_mode == EPI_R_CONST) ? in.R_const : __ldg(in.R + (size_t)kk * in.R_ts); };
+  auto day_pre = [&](int kk) {
+    return in.dot_grp ? __ldg(in.dot_grp + (REV ? (T - 1 - kk) : kk)) : __longlong_as_double(0x7ff8000000000000ll);
+  };
+  double x_nxt = 0.0, R_nxt = 0.0, pre_nxt = 0.0;
+  if (k_begin < k_end) { x_nxt = day_x(k_begin); R_nxt = LEG ? 0.0 : day_R(k_begin); pre_nxt = day_pre(k_begin); }
   for (int k = k_begin; k < k_end; ++k) {
     const int pos = REV ? (T - 1 - k) : k;
+    const double x_cur = x_nxt, R_cur = R_nxt, pre_cur = pre_nxt;
+    if (k + 1 < k_end) { x_nxt = day_x(k + 1); R_nxt = LEG ? 0.0 : day_R(k + 1); pre_nxt = day_pre(k + 1); }
     // :100-101 store the a-priori estimate
     if (EPI_FWD_STORE_COND) {
       double *__restrict__ d = tSm.at_day(pos);
@@ -139,13 +150,13 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
     if (LEG) {
       Rk = (k == 0) ? in.R_const : R_over;  // scalar R adapted in place (:31,:111)
     } else {
-      const double base = (P.r_mode == EPI_R_CONST) ? in.R_const : __ldg(in.R + (size_t)k * in.R_ts);
+      const double base = R_cur;
       Rk = has_over ? R_over : base;
       has_over = false;
     }
     double C[3];
     const double xhat = obs_model<MODEL>(mc.obs_type, s, v_bar, C);  // :115-119
-    const double xk = __ldg(in.x + (size_t)pos * in.x_ts);
+    const double xk = x_cur;
     const bool valid = !(xk != xk);                               // :122
 
     double K[M], sp[M], innov;
@@ -238,7 +249,7 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
     double *uo = P.u_opt.p ? P.u_opt.p + (size_t)P.u_opt.off + b + (size_t)pos * L * P.u_opt.stride : nullptr;
     const double *ud = in.u + (size_t)pos * in.u_ts;
     double dotv, a25 = 0.0;
-    const double pre = in.dot_grp ? __ldg(in.dot_grp + pos) : __longlong_as_double(0x7ff8000000000000ll);
+    const double pre = pre_cur;
     if (pre == pre) {
       dotv = pre;
       if (uo) {
