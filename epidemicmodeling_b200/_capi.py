@@ -56,6 +56,14 @@ class SchedulesArgs(C.Structure):
                 ("prm", _dp), ("seed", C.c_ulonglong), ("first", C.c_longlong), ("u", _dp)]
 
 
+class RtExpFitArgs(C.Structure):
+    _fields_ = [("mem", C.c_int), ("B", C.c_int), ("T", C.c_int), ("G", C.c_int), ("x", _dp), ("s_init", _dp),
+                ("params", _dp), ("w_bar", _dp), ("Ps_init", _dp), ("Q", _dp), ("R", _dp),
+                ("v_bar", C.c_double), ("beta", C.c_double), ("gamma", C.c_double), ("W", C.c_int),
+                ("order", C.c_int), ("S_MINUS", _dp), ("S_PLUS", _dp), ("P_MINUS", _dp), ("P_PLUS", _dp),
+                ("K_GAIN", _dp), ("S_SMOOTH", _dp), ("P_SMOOTH", _dp), ("innovations", _dp), ("rho", _dp)]
+
+
 class NpiCostArgs(C.Structure):
     _fields_ = [("mem", C.c_int), ("B", C.c_int), ("T", C.c_int), ("L", C.c_int), ("G", C.c_int),
                 ("newcases", _dp), ("inputs", _dp), ("weights", _dp), ("J0", _dp), ("J1", _dp)]
@@ -109,6 +117,7 @@ SYMBOLS = {
     "epi_seirp_batch": (C.c_int, [C.c_void_p, C.POINTER(SeirpArgs)]),
     "epi_rollout_cost_batch": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs)]),
     "epi_random_schedules": (C.c_int, [C.c_void_p, C.POINTER(SchedulesArgs)]),
+    "epi_rt_expfit_batch": (C.c_int, [C.c_void_p, C.POINTER(RtExpFitArgs)]),
     "epi_npicost_batch": (C.c_int, [C.c_void_p, C.POINTER(NpiCostArgs)]),
     "epi_si_controlled_batch": (C.c_int, [C.c_void_p, C.POINTER(SiArgs)]),
     "epi_ekf_eks_batch": (C.c_int, [C.c_void_p, C.POINTER(EkfArgs)]),

@@ -106,6 +106,28 @@ def SI_Controlled(alpha, beta, s0, i0, K_, dt):
     return s.reshape(1, K_), i.reshape(1, K_)
 
 
+def Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma, inv_monitor_len, order):
+    """[S_MINUS, S_PLUS, P_MINUS, P_PLUS, K_GAIN, S_SMOOTH, P_SMOOTH, innovations, rho] =
+    Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma, inv_monitor_len, order)
+    -- Tools/Rt_ExpFitEKF.m:1 (x is 1 x T; outputs in the reference's shapes, rho squeezed to T)."""
+    if order not in (1, 2):
+        raise ValueError("Undefined order")                      # Rt_ExpFitEKF.m:47,75
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 2 and x.shape[0] != 1:
+        raise ValueError("Rt_ExpFitEKF: x must be 1 x T (one observation)")
+    x = x.ravel()
+    T = x.size
+    cm = lambda P: np.ascontiguousarray(np.asarray(P, dtype=np.float64).T).ravel()   # column-major page
+    r = get_engine().rt_expfit(x.reshape(T, 1), np.asarray(s_init, dtype=np.float64).reshape(2, 1),
+                               np.asarray(params, dtype=np.float64).ravel()[:3], np.asarray(w_bar, dtype=np.float64).ravel()[:2],
+                               cm(Ps_init), cm(Q_w), np.asarray(R_v, dtype=np.float64).ravel()[:1], T=T, v_bar=float(v_bar),
+                               beta=float(beta), gamma=float(gamma), W=int(inv_monitor_len), order=int(order))
+    P = lambda a: np.transpose(a[:, :, 0].reshape(T, 2, 2), (2, 1, 0)).copy()   # [T][col][row] -> row, col, T
+    return (r["S_MINUS"][:, :, 0].T.copy(), r["S_PLUS"][:, :, 0].T.copy(), P(r["P_MINUS"]), P(r["P_PLUS"]),
+            r["K_GAIN"][:, :, 0].T.reshape(2, 1, T).copy(), r["S_SMOOTH"][:, :, 0].T.copy(), P(r["P_SMOOTH"]),
+            r["innovations"][:, 0].reshape(1, T), r["rho"][:, 0].copy())
+
+
 def NPICost(newcases, inputs, weights):
     """[J0,J1] = NPICost(newcases, inputs, weights)  -- Tools/NPICost.m:1"""
     inp = np.asarray(inputs, dtype=np.float64)

@@ -588,6 +588,58 @@ extern "C" int epi_si_controlled_batch(epi_ctx *c, const epi_si_args *a) {
   });
 }
 
+extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->T < 0 || a->G < 1 || a->W < 1) bad_arg("epi_rt_expfit_batch: bad B/T/G/W");
+    if (a->order != 1 && a->order != 2) bad_arg("Undefined order", EPI_ERR_ORDER);  // Rt_ExpFitEKF.m:47,75
+    if (a->B == 0 || a->T == 0) return;
+    if (!a->x || !a->s_init || !a->params || !a->w_bar || !a->Ps_init || !a->Q || !a->R)
+      bad_arg("epi_rt_expfit_batch: a required array is null");
+    reset_phases(c);
+    const long long B = a->B;
+    const int T = a->T;
+    const long long n_groups = (B + a->G - 1) / a->G;
+    Call shared(c, a->mem);
+    const double *params = shared.in(a->params, (size_t)3 * n_groups);
+    const double *w_bar = shared.in(a->w_bar, (size_t)2 * n_groups);
+    const double *Ps_init = shared.in(a->Ps_init, (size_t)4 * n_groups);
+    const double *Q = shared.in(a->Q, (size_t)4 * n_groups);
+    const double *R = shared.in(a->R, (size_t)n_groups);
+    const size_t per = (size_t)T * (1 + 2 + 2 + 4 + 4 + 2 + 2 + 4 + 1 + 1) * 8 + 16;
+    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, per, scratch_budget(c)) : B;
+    for (long long b0 = 0; b0 < B; b0 += Bw) {
+      const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
+      Call w(c, a->mem);
+      RtParams p{};
+      p.B = (int)nb; p.T = T; p.G = a->G; p.W = a->W; p.order = a->order; p.b0 = b0;
+      p.x = w.traj_in(a->x, T, B, b0, nb);
+      p.s_init = w.traj_in(a->s_init, 2, B, b0, nb);
+      p.params = params; p.w_bar = w_bar; p.Ps_init = Ps_init; p.Q = Q; p.R = R;
+      p.v_bar = a->v_bar; p.beta = a->beta; p.gamma = a->gamma;
+      auto tape = [&](double *out, size_t rows) {
+        return out ? w.traj_out(out, rows, B, b0, nb) : w.scratch(rows, nb);
+      };
+      p.S_MINUS = tape(a->S_MINUS, (size_t)T * 2); p.S_PLUS = tape(a->S_PLUS, (size_t)T * 2);
+      p.P_MINUS = tape(a->P_MINUS, (size_t)T * 4); p.P_PLUS = tape(a->P_PLUS, (size_t)T * 4);
+      p.K_GAIN = w.traj_out(a->K_GAIN, (size_t)T * 2, B, b0, nb);
+      p.S_SMOOTH = w.traj_out(a->S_SMOOTH, (size_t)T * 2, B, b0, nb);
+      p.P_SMOOTH = w.traj_out(a->P_SMOOTH, (size_t)T * 4, B, b0, nb);
+      p.innov = w.traj_out(a->innovations, T, B, b0, nb);
+      p.rho = w.traj_out(a->rho, T, B, b0, nb);
+      // P_SMOOTH without S_SMOOTH still needs the backward pass
+      if (p.P_SMOOTH.p && !p.S_SMOOTH.p) p.S_SMOOTH = w.scratch((size_t)T * 2, nb);
+      PhaseScope ph(c, "rt_expfit");
+      launch_rt_expfit(p, c->stream);
+      check_launch(c, 1);
+      ph.end();
+      w.flush();
+    }
+    finish(c, a->mem);
+  });
+}
+
 // ---------------------------------------------------------------------------
 // EKF + smoother
 // ---------------------------------------------------------------------------

@@ -108,6 +108,22 @@ void launch_rollout(const RolloutParams &p, cudaStream_t st);
 void launch_random_schedules(const epi_model_params *prm, unsigned long long seed, long long first, int B, int K,
                              int L, int G, unsigned char *u, long long stride, long long off, cudaStream_t st);
 
+// Tools/Rt_ExpFitEKF.m (rt_expfit.cu).  Per-trajectory arrays [T][F][B]; per-group tables.
+struct RtParams {
+  int B, T, G, W, order;
+  long long b0;
+  CArr x;                      // [T][B], NaN = missing
+  CArr s_init;                 // [2][B]
+  const double *params;        // per group [3]: time_scale, alpha, sigma
+  const double *w_bar;         // per group [2]
+  const double *Ps_init, *Q;   // per group [4] column-major 2x2
+  const double *R;             // per group [1]
+  double v_bar, beta, gamma;
+  TArr S_MINUS, S_PLUS, P_MINUS, P_PLUS;   // the tape: always present (caller outputs or scratch)
+  TArr K_GAIN, S_SMOOTH, P_SMOOTH, innov, rho;  // optional
+};
+void launch_rt_expfit(const RtParams &p, cudaStream_t st);
+
 struct SiParams {
   int B, K;
   double dt;

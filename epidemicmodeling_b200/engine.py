@@ -311,6 +311,39 @@ class Engine:
             self._done()
         return s, i
 
+    RT_OUTPUTS = ("S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH", "innovations", "rho")
+
+    def rt_expfit(self, x, s_init, params, w_bar, Ps_init, Q, R, *, T, G=1, v_bar=0.0, beta=1.0, gamma=1.0,
+                  W=21, order=1, outputs=RT_OUTPUTS):
+        """Tools/Rt_ExpFitEKF.m for B trajectories: x [T,B], s_init [2,B]; per group of G
+        trajectories params [3] (time_scale, alpha, sigma), w_bar [2], Ps_init / Q [4]
+        column-major, R [1].  Returns {name: array} with S_* [T,2,B], P_* [T,4,B], K_GAIN [T,2,B],
+        innovations / rho [T,B]."""
+        mem = self._mode(x, s_init)
+        B = int(x.shape[-1])
+        ng = (B + G - 1) // G
+        a = K.RtExpFitArgs()
+        a.mem, a.B, a.T, a.G = mem, B, int(T), int(G)
+        a.x = self._in(x, mem, n=T * B)
+        a.s_init = self._in(s_init, mem, n=2 * B)
+        a.params = self._in(params, mem, n=3 * ng)
+        a.w_bar = self._in(w_bar, mem, n=2 * ng)
+        a.Ps_init = self._in(Ps_init, mem, n=4 * ng)
+        a.Q = self._in(Q, mem, n=4 * ng)
+        a.R = self._in(R, mem, n=ng)
+        a.v_bar, a.beta, a.gamma, a.W, a.order = float(v_bar), float(beta), float(gamma), int(W), int(order)
+        shapes = dict(S_MINUS=(T, 2, B), S_PLUS=(T, 2, B), P_MINUS=(T, 4, B), P_PLUS=(T, 4, B), K_GAIN=(T, 2, B),
+                      S_SMOOTH=(T, 2, B), P_SMOOTH=(T, 4, B), innovations=(T, B), rho=(T, B))
+        res = {}
+        for k in outputs:
+            res[k], ptr = self._out(shapes[k], mem)
+            setattr(a, k, ptr)
+        try:
+            self._ck(self._lib.epi_rt_expfit_batch(self._h, C.byref(a)))
+        finally:
+            self._done()
+        return res
+
     # -- EKF + smoother -----------------------------------------------------------
     ALL_OUTPUTS = ("u_opt", "u_opt_smooth", "S_MINUS", "S_PLUS", "S_SMOOTH", "P_MINUS", "P_PLUS",
                    "P_SMOOTH", "K_GAIN", "innovations", "rho")

@@ -201,6 +201,27 @@ typedef struct {
 } epi_si_args;
 int epi_si_controlled_batch(epi_ctx *ctx, const epi_si_args *a);
 
+/* Exponential-fit EKF / smoother -------------------------------------------------
+ * replaces  [S_MINUS, S_PLUS, P_MINUS, P_PLUS, K_GAIN, S_SMOOTH, P_SMOOTH, innovations, rho] =
+ *              Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma,
+ *              inv_monitor_len, order)                          Tools/Rt_ExpFitEKF.m:1
+ * (2 states: new cases and growth exponent; order 2 adds the second-order Hessian terms of
+ * Rt_ExpFitEKF.m:153-196; order outside {1,2} returns EPI_ERR_ORDER, :47).  x [T][B] (NaN =
+ * missing), s_init [2][B]; params = {time_scale, alpha, sigma} [3], w_bar [2], Ps_init / Q_w
+ * [4] column-major and R_v [1] per group of G trajectories.  Outputs per trajectory, each
+ * optional: S_* [T][2][B], P_* [T][4][B] (column-major pages), K_GAIN [T][2][B],
+ * innovations [T][B], rho [T][B]. */
+typedef struct {
+  int mem;
+  int B, T, G;
+  const double *x, *s_init;
+  const double *params, *w_bar, *Ps_init, *Q, *R;
+  double v_bar, beta, gamma;
+  int W, order;
+  double *S_MINUS, *S_PLUS, *P_MINUS, *P_PLUS, *K_GAIN, *S_SMOOTH, *P_SMOOTH, *innovations, *rho;
+} epi_rt_expfit_args;
+int epi_rt_expfit_batch(epi_ctx *ctx, const epi_rt_expfit_args *a);
+
 /* EKF + fixed-interval smoother ------------------------------------------------
  * replaces  GenericExtendedKalmanFilter(u, x, handles, params, s_init, Ps_init,
  *              s_final, Ps_final, w_bar, v_bar, Q_w, R_v, beta, gamma,

@@ -142,6 +142,35 @@ static void cmd_si(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   if (nlhs > 1) plhs[1] = oi; else mxDestroyArray(oi);
 }
 
+// [S_MINUS, S_PLUS, P_MINUS, P_PLUS, K_GAIN, S_SMOOTH, P_SMOOTH, innovations, rho] =
+//   epi_mex('rt_expfit', x(1xT), s_init(2x1), params(3x1), w_bar(2x1), v_bar, Ps_init(2x2), Q_w(2x2), R_v, beta,
+//           gamma, inv_monitor_len, order)                                   Tools/Rt_ExpFitEKF.m:1
+static void cmd_rt_expfit(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+  if (nrhs < 12) mexErrMsgIdAndTxt("epi:arg", "rt_expfit: 12 arguments expected");
+  epi_rt_expfit_args a;
+  std::memset(&a, 0, sizeof a);
+  const double R = scalar(prhs[7]);
+  a.mem = EPI_MEM_HOST; a.B = 1; a.G = 1; a.T = (int)mxGetNumberOfElements(prhs[0]);
+  a.x = dbl(prhs[0]); a.s_init = dbl(prhs[1]); a.params = dbl(prhs[2]); a.w_bar = dbl(prhs[3]);
+  a.v_bar = scalar(prhs[4]); a.Ps_init = dbl(prhs[5]); a.Q = dbl(prhs[6]); a.R = &R;   // 2x2 pages are column-major on both sides
+  a.beta = scalar(prhs[8]); a.gamma = scalar(prhs[9]); a.W = (int)scalar(prhs[10]); a.order = (int)scalar(prhs[11]);
+  const mwSize T = (mwSize)a.T, d3[3] = {2, 2, T}, k3[3] = {2, 1, T};
+  mxArray *o[9];
+  o[0] = mxCreateDoubleMatrix(2, T, mxREAL); o[1] = mxCreateDoubleMatrix(2, T, mxREAL);
+  o[2] = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL); o[3] = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
+  o[4] = mxCreateNumericArray(3, k3, mxDOUBLE_CLASS, mxREAL);
+  o[5] = mxCreateDoubleMatrix(2, T, mxREAL); o[6] = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
+  o[7] = mxCreateDoubleMatrix(1, T, mxREAL); o[8] = mxCreateDoubleMatrix(T, 1, mxREAL);
+  a.S_MINUS = mxGetPr(o[0]); a.S_PLUS = mxGetPr(o[1]); a.P_MINUS = mxGetPr(o[2]); a.P_PLUS = mxGetPr(o[3]);
+  a.K_GAIN = mxGetPr(o[4]); a.S_SMOOTH = mxGetPr(o[5]); a.P_SMOOTH = mxGetPr(o[6]);
+  a.innovations = mxGetPr(o[7]); a.rho = mxGetPr(o[8]);
+  check(epi_rt_expfit_batch(ctx(), &a));   // B = 1: [T][F][1] is MATLAB's column-major F x T
+  const int want = nlhs > 0 ? nlhs : 1;
+  for (int f = 0; f < 9; ++f) {
+    if (f < want) plhs[f] = o[f]; else mxDestroyArray(o[f]);
+  }
+}
+
 // [J0,J1] = epi_mex('npicost', newcases(1xT), inputs(LxT), weights(LxT))
 static void cmd_npicost(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   if (nrhs < 3) mexErrMsgIdAndTxt("epi:arg", "npicost: 3 arguments expected");
@@ -295,6 +324,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   else if (c == "sialpha_controlled") cmd_rollout(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "si_controlled") cmd_si(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "npicost") cmd_npicost(nlhs, plhs, nrhs - 1, prhs + 1);
+  else if (c == "rt_expfit") cmd_rt_expfit(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "pareto") cmd_pareto(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "ekf_eks") cmd_ekf(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "sweep") cmd_sweep(nlhs, plhs, nrhs - 1, prhs + 1);

@@ -1078,3 +1078,148 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------- */
+/* Rt_ExpFitEKF: 2-state exponential-fit EKF/EKS with second-order terms     */
+/* (Tools/Rt_ExpFitEKF.m:1-227) -- SURVEY 8f-3                               */
+/* ------------------------------------------------------------------------- */
+/* 2x2 matrices are row-major double[4] = {m11, m12, m21, m22}.  Products are DEFINED as
+ * c_ij = fma(a_i2, b_2j, a_i1 * b_1j) with every term kept (structural zeros included:
+ * exact for finite operands), as the arithmetic contract of DESIGN.md states. */
+static void mm2(const double *a, const double *b, double *c) {
+  double t[4];
+  t[0] = fma(a[1], b[2], a[0] * b[0]); t[1] = fma(a[1], b[3], a[0] * b[1]);
+  t[2] = fma(a[3], b[2], a[2] * b[0]); t[3] = fma(a[3], b[3], a[2] * b[1]);
+  c[0] = t[0]; c[1] = t[1]; c[2] = t[2]; c[3] = t[3];
+}
+static void tr2(const double *a, double *t) { t[0] = a[0]; t[1] = a[2]; t[2] = a[1]; t[3] = a[3]; }
+/* trace(P*Fi*P*Fj)/2 evaluated left to right (:178) */
+static double half_trace4(const double *P, const double *Fi, const double *Fj) {
+  double a[4], b[4], c[4];
+  mm2(P, Fi, a); mm2(a, P, b); mm2(b, Fj, c);
+  return (c[0] + c[3]) / 2.0;
+}
+static double half_trace2(const double *P, const double *F) {
+  double a[4];
+  mm2(P, F, a);
+  return (a[0] + a[3]) / 2.0;
+}
+
+/* x[T] (NaN = missing), s_init[2], params[3] = {time_scale, alpha, sigma} (:121-123), w_bar[2],
+ * Ps_init / Q row-major 2x2, scalar R.  Outputs (any may be NULL except the four tape arrays):
+ * S_* [T][2], P_* [T][4] row-major, K_GAIN [T][2], innovations [T], rho [T].
+ * Returns 0, or -2 for order not in {1,2} (:47,:75 'Undefined order'). */
+int orc_rt_expfit_ekf(const double *x, int T, const double *s_init, const double *params, const double *w_bar,
+                      double v_bar, const double *Ps_init, const double *Q, double R, double beta, double gamma,
+                      int W, int order, double *S_MINUS, double *S_PLUS, double *P_MINUS, double *P_PLUS,
+                      double *K_GAIN, double *S_SMOOTH, double *P_SMOOTH, double *innovations, double *rho) {
+  if (order != 1 && order != 2) return -2;
+  const double ts = params[0], alpha = params[1], sigma = params[2];
+  double sm[2] = {s_init[0], s_init[1]}, Pm[4] = {Ps_init[0], Ps_init[1], Ps_init[2], Ps_init[3]};
+  double *winM = (double *)calloc((size_t)3 * W, sizeof(double)), *winC = winM + W, *winN = winM + 2 * W;
+  for (int k = 0; k < T; ++k) {
+    S_MINUS[2 * k] = sm[0]; S_MINUS[2 * k + 1] = sm[1];                 /* :37-38 */
+    for (int q = 0; q < 4; ++q) P_MINUS[4 * k + q] = Pm[q];
+    /* :40-49 observation Hessian terms: Gs = Gv = {0} => gs = Gsp = gv = Gvp = 0 for either order */
+    const double xhat = (sm[0] + v_bar) + 0.0 + 0.0;                       /* :53, :131 */
+    double innov, Kg[2], sp[2], Pp[4];
+    if (!(x[k] != x[k])) {                                                 /* :56 */
+      innov = x[k] - xhat;                                                 /* :57 */
+      const double denom = ((Pm[0] + gamma * ((1.0 * R) * 1.0)) + 0.0) + 0.0; /* :58, C = [1 0], D = 1 */
+      Kg[0] = Pm[0] / denom; Kg[1] = Pm[2] / denom;
+      const double M[4] = {1.0 - Kg[0], 0.0 - 0.0, 0.0 - Kg[1], 1.0 - 0.0}; /* eye(m) - Kgain*C */
+      double MP[4];
+      mm2(M, Pm, MP);
+      for (int q = 0; q < 4; ++q) Pp[q] = MP[q] / gamma;                   /* :59 */
+      sp[0] = sm[0] + Kg[0] * innov; sp[1] = sm[1] + Kg[1] * innov;        /* :60 */
+    } else {                                                               /* :62-65 */
+      innov = 0.0; Kg[0] = Kg[1] = 0.0;
+      for (int q = 0; q < 4; ++q) Pp[q] = Pm[q];
+      sp[0] = sm[0]; sp[1] = sm[1];
+    }
+    const double E = exp(ts * sp[1]);
+    const double tnh = tanh((alpha * sp[1] + w_bar[1]) / sigma);
+    double fs[2] = {0, 0}, fw[2] = {0, 0}, Fsp[4] = {0, 0, 0, 0}, Fwp[4] = {0, 0, 0, 0};
+    if (order == 2) {                                                      /* :153-196 */
+      const double f12 = ts * E;
+      const double Fs1[4] = {0.0, f12, f12, ((ts * ts) * sp[0]) * E};
+      const double Fs2[4] = {0.0, 0.0, 0.0, ((((-2.0) * (alpha * alpha)) / sigma) * tnh) * (1.0 - tnh * tnh)};
+      const double Fw1[4] = {0.0, 0.0, 0.0, 0.0};
+      const double Fw2[4] = {0.0, 0.0, 0.0, (((-2.0) / sigma) * tnh) * (1.0 - tnh * tnh)};
+      const double *Fs[2] = {Fs1, Fs2}, *Fw[2] = {Fw1, Fw2};
+      for (int i = 0; i < 2; ++i) {
+        fs[i] = half_trace2(Pp, Fs[i]);
+        fw[i] = half_trace2(Q, Fw[i]);
+        for (int j = 0; j < 2; ++j) {
+          Fsp[2 * i + j] = half_trace4(Pp, Fs[i], Fs[j]);
+          Fwp[2 * i + j] = half_trace4(Q, Fw[i], Fw[j]);
+        }
+      }
+    }
+    /* :80 state update (:120-127) + second-order means */
+    sm[0] = ((sp[0] * E + w_bar[0]) + fs[0]) + fw[0];
+    sm[1] = ((sigma * tnh) + fs[1]) + fw[1];
+    /* :81-82 */
+    const double omt = 1.0 - tnh * tnh;
+    const double A[4] = {E, (ts * sp[0]) * E, 0.0, alpha * omt};
+    const double Bm[4] = {1.0, 0.0, 0.0, omt};
+    double At[4], Bt[4], AP[4], APA[4], BQ[4], BQB[4];
+    tr2(A, At); tr2(Bm, Bt);
+    mm2(A, Pp, AP); mm2(AP, At, APA);
+    mm2(Bm, Q, BQ); mm2(BQ, Bt, BQB);
+    for (int q = 0; q < 4; ++q) Pm[q] = ((APA[q] + BQB[q]) + Fsp[q]) + Fwp[q];
+    S_PLUS[2 * k] = sp[0]; S_PLUS[2 * k + 1] = sp[1];                      /* :85-87 */
+    for (int q = 0; q < 4; ++q) P_PLUS[4 * k + q] = Pp[q];
+    if (K_GAIN) { K_GAIN[2 * k] = Kg[0]; K_GAIN[2 * k + 1] = Kg[1]; }
+    if (innovations) innovations[k] = innov;
+    /* :90-101 innovation monitor, windows newest first */
+    const int cnt = (k + 1 < W) ? (k + 1) : W;
+    for (int j = W - 1; j > 0; --j) { winM[j] = winM[j - 1]; winC[j] = winC[j - 1]; winN[j] = winN[j - 1]; }
+    winM[0] = innov;
+    double sM = 0.0;
+    for (int j = 0; j < W; ++j) sM += winM[j];
+    const double mu = sM / (double)cnt;
+    const double cc = (innov - mu) * (innov - mu);
+    winC[0] = cc;
+    winN[0] = cc / R;                                                      /* :97 (no eps) */
+    double sN = 0.0;
+    for (int j = 0; j < W; ++j) sN += winN[j];
+    if (rho) rho[k] = sN / (double)cnt;
+    if (beta != 1.0 && !(x[k] != x[k])) {                                  /* :99-101 */
+      double sC = 0.0;
+      for (int j = 0; j < W; ++j) sC += winC[j];
+      R = beta * R + ((1.0 - beta) * sC) / (double)cnt;
+    }
+  }
+  free(winM);
+  /* :104-115 smoother */
+  if (S_SMOOTH && T > 0) {
+    double ss[2] = {S_PLUS[2 * (T - 1)], S_PLUS[2 * (T - 1) + 1]}, Ps[4];
+    for (int q = 0; q < 4; ++q) Ps[q] = P_PLUS[4 * (T - 1) + q];
+    S_SMOOTH[2 * (T - 1)] = ss[0]; S_SMOOTH[2 * (T - 1) + 1] = ss[1];
+    if (P_SMOOTH) for (int q = 0; q < 4; ++q) P_SMOOTH[4 * (T - 1) + q] = Ps[q];
+    for (int k = T - 2; k >= 0; --k) {
+      const double *sp = S_PLUS + 2 * k, *Pp = P_PLUS + 4 * k, *Pn = P_MINUS + 4 * (k + 1), *sn = S_MINUS + 2 * (k + 1);
+      const double E = exp(ts * sp[1]);
+      const double tnh = tanh((alpha * sp[1] + w_bar[1]) / sigma);
+      const double A[4] = {E, (ts * sp[0]) * E, 0.0, alpha * (1.0 - tnh * tnh)};
+      double At[4], PAt[4], Bc[4], Ac[4], Jc[4], J[4];
+      tr2(A, At); mm2(Pp, At, PAt);
+      /* orc_mrdivide takes column-major m x m */
+      Bc[0] = PAt[0]; Bc[1] = PAt[2]; Bc[2] = PAt[1]; Bc[3] = PAt[3];
+      Ac[0] = Pn[0]; Ac[1] = Pn[2]; Ac[2] = Pn[1]; Ac[3] = Pn[3];
+      orc_mrdivide(Bc, Ac, 2, Jc);                                         /* :110 */
+      J[0] = Jc[0]; J[1] = Jc[2]; J[2] = Jc[1]; J[3] = Jc[3];
+      const double d0 = ss[0] - sn[0], d1 = ss[1] - sn[1];
+      const double n0 = sp[0] + fma(J[1], d1, J[0] * d0), n1 = sp[1] + fma(J[3], d1, J[2] * d0); /* :111 */
+      double D[4], Jt[4], JD[4], JDJ[4];
+      for (int q = 0; q < 4; ++q) D[q] = Pn[q] - Ps[q];
+      tr2(J, Jt); mm2(J, D, JD); mm2(JD, Jt, JDJ);
+      for (int q = 0; q < 4; ++q) Ps[q] = Pp[q] - JDJ[q];                  /* :112 */
+      ss[0] = n0; ss[1] = n1;
+      S_SMOOTH[2 * k] = ss[0]; S_SMOOTH[2 * k + 1] = ss[1];
+      if (P_SMOOTH) for (int q = 0; q < 4; ++q) P_SMOOTH[4 * k + q] = Ps[q];
+    }
+  }
+  return 0;
+}

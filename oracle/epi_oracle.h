@@ -104,6 +104,12 @@ void orc_npicost(const double *newcases, int T, const double *inputs, const doub
  * knee index (0-based; first minimum, NaN skipped as MATLAB's min does). */
 void orc_pareto(const double *J0, const double *J1, int n, unsigned char *on_front, int *I_opt);
 
+/* Tools/Rt_ExpFitEKF.m: 2-state exponential-fit EKF/EKS with second-order (Hessian) terms */
+int orc_rt_expfit_ekf(const double *x, int T, const double *s_init, const double *params, const double *w_bar,
+                      double v_bar, const double *Ps_init, const double *Q, double R, double beta, double gamma,
+                      int W, int order, double *S_MINUS, double *S_PLUS, double *P_MINUS, double *P_PLUS,
+                      double *K_GAIN, double *S_SMOOTH, double *P_SMOOTH, double *innovations, double *rho);
+
 /* random NPI schedules (TrainPredictPrescribeNPI.m:499-510) on a Philox4x32-10 counter stream */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_random_schedule(uint64_t seed, uint32_t region, uint32_t scenario, int n_scenarios, int L, int K,

@@ -186,6 +186,29 @@ def random_schedule(seed, region, scenario, n_scenarios, L, K, u_min, u_max):
     return u.T.copy()
 
 
+def Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma, inv_monitor_len, order):
+    """Tools/Rt_ExpFitEKF.m:1 -- returns the 9 outputs in the reference's order and shapes."""
+    x = _f(x).ravel()
+    T = x.size
+    o = dict(S_MINUS=np.zeros((T, 2)), S_PLUS=np.zeros((T, 2)), P_MINUS=np.zeros((T, 4)), P_PLUS=np.zeros((T, 4)),
+             K_GAIN=np.zeros((T, 2)), S_SMOOTH=np.zeros((T, 2)), P_SMOOTH=np.zeros((T, 4)),
+             innovations=np.zeros(T), rho=np.zeros(T))
+    lib().orc_rt_expfit_ekf.restype = C.c_int
+    rc = lib().orc_rt_expfit_ekf(
+        _p(x), C.c_int(T), _p(_f(s_init).ravel()), _p(_f(params).ravel()), _p(_f(w_bar).ravel()),
+        C.c_double(float(v_bar)), _p(_f(np.asarray(Ps_init, dtype=np.float64)).ravel()),
+        _p(_f(np.asarray(Q_w, dtype=np.float64)).ravel()), C.c_double(float(np.asarray(R_v).ravel()[0])),
+        C.c_double(float(beta)), C.c_double(float(gamma)), C.c_int(int(inv_monitor_len)), C.c_int(int(order)),
+        *[_p(o[k]) for k in ("S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH",
+                             "innovations", "rho")])
+    if rc == -2:
+        raise ValueError("Undefined order")
+    P = lambda a: np.transpose(a.reshape(T, 2, 2), (1, 2, 0)).copy()     # [T][row][col] -> 2 x 2 x T
+    return (o["S_MINUS"].T.copy(), o["S_PLUS"].T.copy(), P(o["P_MINUS"]), P(o["P_PLUS"]),
+            o["K_GAIN"].T.reshape(2, 1, T).copy(), o["S_SMOOTH"].T.copy(), P(o["P_SMOOTH"]),
+            o["innovations"].reshape(1, T), o["rho"].reshape(T))
+
+
 def pareto(J0, J1):
     J0, J1 = _f(J0).ravel(), _f(J1).ravel()
     n = J0.size

@@ -143,3 +143,18 @@ def sweep_case(n_regions=3, n_eps=12, T_hist=60, T_fore=30):
     inp = syn.sweep_inputs(n_regions=n_regions, T_hist=T_hist, T_fore=T_fore)
     eps = syn.epsilon_grid_xprize02(250)[:: max(1, 250 // n_eps)][:n_eps].copy()
     return inp, eps
+
+
+def rt_expfit_case(T=220, seed=4, order=1, forecast_days=14):
+    """Rt_ExpFitEKF call of testScripts/test04FullFeatureExtMLpipeline.m:198-219 on a synthetic
+    smoothed new-case series (exponential growth/decay with a slowly varying exponent)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(T)
+    lam = 0.06 * np.sin(t / 35.0) + 0.01
+    x = 800.0 * np.exp(np.cumsum(lam)) * (1.0 + 0.04 * rng.standard_normal(T))
+    x[T - forecast_days:] = np.nan                               # :201 masked forecast horizon
+    x[40:43] = np.nan                                            # a reporting gap
+    Q_w = np.diag([250.0 ** 2, 3.0e-3 ** 2])
+    return dict(x=x.reshape(1, T), s_init=np.array([x[0], lam[0]]), params=np.array([1.0, 0.9, 0.1]),
+                w_bar=np.zeros(2), v_bar=0.0, Ps_init=100.0 * Q_w, Q_w=Q_w, R_v=10.0 ** 2, beta=0.9,
+                gamma=0.995, inv_monitor_len=21, order=order)

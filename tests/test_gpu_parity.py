@@ -397,6 +397,47 @@ def test_generated_schedules_match_oracle_and_supplied(engine, nS):
         engine.rollout_cost(bad, x0, None, Kn, L, B=B, seed=seed, **kw)            # level bounds are required
 
 
+# ------------------------------------------------------------------------------ Rt_ExpFitEKF
+TOL_RT = 1e-9   # north_star tolerance for EKF states; exp/tanh are not correctly rounded on either side
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_rt_expfit_signature_mirror(order):
+    """api.Rt_ExpFitEKF (Tools/Rt_ExpFitEKF.m:1 signature) against the oracle."""
+    c = cases.rt_expfit_case(order=order)
+    got, ref = api.Rt_ExpFitEKF(**c), orc().Rt_ExpFitEKF(**c)
+    names = ("S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH", "innovations", "rho")
+    for n, a, b in zip(names, got, ref):
+        assert a.shape == b.shape, n
+        scale = np.max(np.abs(b)) or 1.0
+        assert np.max(np.abs(a - b)) / scale <= TOL_RT, f"{n}: {np.max(np.abs(a - b)) / scale:.2e}"
+    with pytest.raises(ValueError, match="Undefined order"):
+        api.Rt_ExpFitEKF(**dict(c, order=0))
+
+
+def test_rt_expfit_batch(engine):
+    """A batch of series with per-group parameters, ragged block (B = 70 > one 64-thread CTA),
+    outputs on request only."""
+    B, G, T = 70, 35, 150
+    cs = [cases.rt_expfit_case(T=T, seed=100 + b, order=2) for b in range(B)]
+    x = np.stack([c["x"][0] for c in cs], axis=1)
+    s0 = np.stack([c["s_init"] for c in cs], axis=1)
+    prm = np.array([[1.0, 0.9, 0.1], [1.0, 0.8, 0.2]])
+    Qs = [np.diag([250.0 ** 2, 3.0e-3 ** 2]), np.diag([100.0 ** 2, 5.0e-3 ** 2])]
+    res = engine.rt_expfit(x, s0, prm, np.zeros((2, 2)), np.stack([(100 * q).T.ravel() for q in Qs]),
+                           np.stack([q.T.ravel() for q in Qs]), np.array([100.0, 400.0]), T=T, G=G, beta=0.9,
+                           gamma=0.995, W=21, order=2, outputs=("S_SMOOTH", "rho"))
+    assert set(res) == {"S_SMOOTH", "rho"}
+    o = orc()
+    for b in (0, 34, 35, 69):
+        g = b // G
+        ref = o.Rt_ExpFitEKF(x[:, b], s0[:, b], prm[g], [0, 0], 0.0, 100 * Qs[g], Qs[g], [100.0, 400.0][g], 0.9, 0.995, 21, 2)
+        for a, r in ((res["S_SMOOTH"][:, :, b].T, ref[5]), (res["rho"][:, b], ref[8])):
+            assert np.max(np.abs(a - r)) / np.max(np.abs(r)) <= TOL_RT
+    with pytest.raises(K.EpiError):
+        engine.rt_expfit(x, s0, prm, np.zeros((2, 2)), np.zeros((2, 4)), np.zeros((2, 4)), np.ones(2), T=T, G=G, order=3)
+
+
 # ------------------------------------------------------------------------------ fused sweep
 def _run_sweep(engine, inp, eps, **kw):
     S = wl.run_fixed_input(engine, inp)

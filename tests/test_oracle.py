@@ -346,3 +346,87 @@ def test_random_schedule_rule():
     cnt = np.bincount(lv, minlength=4)
     chi2 = ((cnt - lv.size / 4) ** 2 / (lv.size / 4)).sum()
     assert chi2 < 16.3                              # p = 0.001
+
+
+# ---------------------------------------------------------------------------- Rt_ExpFitEKF
+def _rt_twin(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma, W, order):
+    """Independent NumPy transliteration of Tools/Rt_ExpFitEKF.m (matrix products through BLAS,
+    mrdivide through numpy.linalg.solve, windows through np.concatenate as the .m's cat())."""
+    x = np.asarray(x, float).reshape(1, -1)
+    T, m = x.shape[1], 2
+    ts, al, sg = params
+    S_M, S_P = np.zeros((m, T)), np.zeros((m, T))
+    P_M, P_P = np.zeros((m, m, T)), np.zeros((m, m, T))
+    rho = np.zeros(T)
+    s, P, Q, R = np.asarray(s_init, float).copy(), np.asarray(Ps_init, float).copy(), np.asarray(Q_w, float), float(R_v)
+    wM, wC, wN = np.zeros(W), np.zeros(W), np.zeros(W)
+    C = np.array([[1.0, 0.0]])
+    f = lambda s: np.array([s[0] * np.exp(ts * s[1]) + w_bar[0], sg * np.tanh((al * s[1] + w_bar[1]) / sg)])
+
+    def jac(s):
+        tn = np.tanh((al * s[1] + w_bar[1]) / sg)
+        A = np.array([[np.exp(ts * s[1]), ts * s[0] * np.exp(ts * s[1])], [0.0, al * (1 - tn ** 2)]])
+        return A, np.diag([1.0, 1 - tn ** 2]), tn
+    for k in range(T):
+        S_M[:, k], P_M[:, :, k] = s, P
+        if not np.isnan(x[0, k]):
+            inn = x[0, k] - (s[0] + v_bar)
+            Kg = P @ C.T / (C @ P @ C.T + gamma * R)
+            Pp = (np.eye(2) - Kg @ C) @ P / gamma
+            sp = s + Kg[:, 0] * inn
+        else:
+            inn, Pp, sp = 0.0, P, s
+        A, Bm, tn = jac(sp)
+        fs = fw = np.zeros(2); Fsp = Fwp = np.zeros((2, 2))
+        if order == 2:
+            E = np.exp(ts * sp[1])
+            Fs = [np.array([[0, ts * E], [ts * E, ts ** 2 * sp[0] * E]]), np.array([[0, 0], [0, -2 * al ** 2 / sg * tn * (1 - tn ** 2)]])]
+            Fw = [np.zeros((2, 2)), np.array([[0, 0], [0, -2 / sg * tn * (1 - tn ** 2)]])]
+            fs = np.array([np.trace(Pp @ F) / 2 for F in Fs]); fw = np.array([np.trace(Q @ F) / 2 for F in Fw])
+            Fsp = np.array([[np.trace(Pp @ Fi @ Pp @ Fj) / 2 for Fj in Fs] for Fi in Fs])
+            Fwp = np.array([[np.trace(Q @ Fi @ Q @ Fj) / 2 for Fj in Fw] for Fi in Fw])
+        s = f(sp) + fs + fw
+        P = A @ Pp @ A.T + Bm @ Q @ Bm.T + Fsp + Fwp
+        S_P[:, k], P_P[:, :, k] = sp, Pp
+        cnt = min(k + 1, W)
+        wM = np.concatenate([[inn], wM[:-1]]); mu = wM.sum() / cnt
+        cc = (inn - mu) ** 2
+        wC = np.concatenate([[cc], wC[:-1]]); wN = np.concatenate([[cc / R], wN[:-1]])
+        rho[k] = wN.sum() / cnt
+        if beta != 1 and not np.isnan(x[0, k]):
+            R = beta * R + (1 - beta) * wC.sum() / cnt
+    S_S, P_S = S_P.copy(), P_P.copy()
+    for k in range(T - 2, -1, -1):
+        A = jac(S_P[:, k])[0]
+        J = np.linalg.solve(P_M[:, :, k + 1].T, (P_P[:, :, k] @ A.T).T).T
+        S_S[:, k] = S_P[:, k] + J @ (S_S[:, k + 1] - S_M[:, k + 1])
+        P_S[:, :, k] = P_P[:, :, k] - J @ (P_M[:, :, k + 1] - P_S[:, :, k + 1]) @ J.T
+    return S_M, S_P, P_M, P_P, S_S, P_S, rho
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_rt_expfit_oracle_matches_numpy_twin(order):
+    c = cases.rt_expfit_case(order=order)
+    out = orc.Rt_ExpFitEKF(**c)
+    tw = _rt_twin(c["x"], c["s_init"], c["params"], c["w_bar"], c["v_bar"], c["Ps_init"], c["Q_w"], c["R_v"],
+                  c["beta"], c["gamma"], c["inv_monitor_len"], order)
+    for name, a, b in (("S_MINUS", out[0], tw[0]), ("S_PLUS", out[1], tw[1]), ("P_MINUS", out[2], tw[2]),
+                       ("P_PLUS", out[3], tw[3]), ("S_SMOOTH", out[5], tw[4]), ("P_SMOOTH", out[6], tw[5]),
+                       ("rho", out[8], tw[6])):
+        assert rel(a, b, 1e-300) < 1e-9, name
+    T = c["x"].shape[1]
+    assert out[4].shape == (2, 1, T) and out[7].shape == (1, T) and out[8].shape == (T,)
+    miss = np.isnan(c["x"][0])
+    assert not out[4][:, 0, miss].any() and not out[7][0, miss].any()      # :62-65 K = 0, innovation = 0
+    assert np.array_equal(out[3][:, :, miss], out[2][:, :, miss])          # P+ = P- without the 1/gamma
+    assert np.array_equal(out[5][:, -1], out[1][:, -1])                    # :105
+    assert np.max(np.abs(out[5][1])) < c["params"][2]                      # |lambda| < sigma (tanh saturation)
+
+
+def test_rt_expfit_second_order_terms_and_order_check():
+    c1, c2 = cases.rt_expfit_case(order=1), cases.rt_expfit_case(order=2)
+    o1, o2 = orc.Rt_ExpFitEKF(**c1), orc.Rt_ExpFitEKF(**c2)
+    d = np.abs(o1[5] - o2[5]).max(axis=1) / np.abs(o1[5]).max(axis=1)
+    assert 1e-9 < d[0] < 1e-1 and 1e-9 < d[1] < 1e-1      # the Hessian terms act, as a small correction
+    with pytest.raises(ValueError, match="Undefined order"):
+        orc.Rt_ExpFitEKF(**dict(c1, order=3))
