@@ -113,6 +113,61 @@ class ClockSampler:
         return out
 
 
+class NvmlSampler:
+    """The same samples through NVML (nvidia_ml_py) from a thread: a query takes well under a
+    millisecond, so even a 100 ms timed region gets dozens of samples (the nvidia-smi process above
+    needs longer than that just to start).  Falls back to ClockSampler when NVML is unavailable."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def __init__(self, index):
+        self.index, self.h, self.fallback = index, None, None
+        self.sm, self.mx, self.mask, self._stop, self.thread = [], None, 0, threading.Event(), None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:  # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: go through the UUID
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h, self.fallback = None, ClockSampler(index)
+
+    def _one(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.mask |= int(get(self.h))
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._one()
+            except Exception:
+                pass
+            self._stop.wait(0.004)
+
+    def start(self):
+        if self.fallback:
+            return self.fallback.start()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.fallback:
+            return self.fallback.stop()
+        self._stop.set()
+        self.thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": len(self.sm), "source": "nvml"}
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
+            out["reasons"] = sorted(name for bit, name in self.REASONS if self.mask & bit)
+        return out
+
+
 def build_inputs(a, rank):
     from epidemicmodeling_b200 import synthetic as syn
     # weak scaling: every rank gets its own 236-region replica (different seeds)
@@ -254,7 +309,7 @@ def main():
     fence()
     launches0 = eng.launch_count
     ktimes = {}
-    sampler = ClockSampler(local)
+    sampler = NvmlSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()

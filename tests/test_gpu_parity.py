@@ -221,6 +221,26 @@ def test_ekf_signatures_bit_exact(engine, name):
         assert_bits(got[k], g[k], f"{name}.{k} vs golden")
 
 
+@pytest.mark.parametrize("log2_scale", [-960, 490])
+@pytest.mark.parametrize("which", ["ekf3", "ekf6"])
+def test_extreme_covariance_scales_take_the_slow_paths(engine, which, log2_scale):
+    """Scaling Ps_init, Q_w, R_v (and a finite Ps_final) by 2^k scales every covariance exactly and
+    leaves gains and states alone -- but at 2^-960 / 2^490 the squares inside the Jacobi angle and the
+    quotients of the covariance update leave the exponent window of the fast paths (branch-free
+    3-wide div/sqrt, reciprocal division), so the kernels must take their true-division / textbook
+    fall-backs.  Same bits as the oracle there too."""
+    f = 2.0 ** log2_scale
+    c = cases.ekf3_case(0) if which == "ekf3" else cases.ekf6_case(0)
+    c = dict(c, Ps_init=np.asarray(c["Ps_init"]) * f, Q_w=np.asarray(c["Q_w"]) * f, R_v=np.asarray(c["R_v"]) * f,
+             Ps_final=np.asarray(c["Ps_final"]) * f)
+    fn, model = (api.SIAlphaModelEKF, 0) if which == "ekf3" else (api.SIAlphaModelEKFOptControlled, 2)
+    got = dict(zip(EKF_KEYS, fn(*ekf_args(c))))
+    want = orc().ekf_eks(model, *ekf_args(c))
+    for k in EKF_KEYS:
+        assert_bits(got[k], want[k], f"{which} x 2^{log2_scale}: {k}")
+    assert np.isfinite(got["S_SMOOTH"]).all() and np.isfinite(got["P_SMOOTH"]).all()
+
+
 @pytest.mark.parametrize("variant", ["tools", "codegen"])
 def test_legacy_estimator_bit_exact(engine, variant):
     c = cases.legacy_case(0 if variant == "tools" else 1)
