@@ -64,6 +64,13 @@ class RtExpFitArgs(C.Structure):
                 ("K_GAIN", _dp), ("S_SMOOTH", _dp), ("P_SMOOTH", _dp), ("innovations", _dp), ("rho", _dp)]
 
 
+class PreprocessArgs(C.Structure):
+    _fields_ = [("mem", C.c_int), ("B", C.c_int), ("T", C.c_int), ("L", C.c_int), ("W", C.c_int),
+                ("n_first", C.c_int), ("min_cases", C.c_double), ("cc", _dp), ("population", _dp), ("ip", _dp),
+                ("ip_filled", _dp), ("refined", _dp), ("smoothed", _dp), ("zerolag", _dp), ("normalized", _dp),
+                ("confirmed_norm", _dp), ("R_v", _dp), ("I0", _dp)]
+
+
 class NpiCostArgs(C.Structure):
     _fields_ = [("mem", C.c_int), ("B", C.c_int), ("T", C.c_int), ("L", C.c_int), ("G", C.c_int),
                 ("newcases", _dp), ("inputs", _dp), ("weights", _dp), ("J0", _dp), ("J1", _dp)]
@@ -118,6 +125,7 @@ SYMBOLS = {
     "epi_rollout_cost_batch": (C.c_int, [C.c_void_p, C.POINTER(RolloutArgs)]),
     "epi_random_schedules": (C.c_int, [C.c_void_p, C.POINTER(SchedulesArgs)]),
     "epi_rt_expfit_batch": (C.c_int, [C.c_void_p, C.POINTER(RtExpFitArgs)]),
+    "epi_preprocess_batch": (C.c_int, [C.c_void_p, C.POINTER(PreprocessArgs)]),
     "epi_npicost_batch": (C.c_int, [C.c_void_p, C.POINTER(NpiCostArgs)]),
     "epi_si_controlled_batch": (C.c_int, [C.c_void_p, C.POINTER(SiArgs)]),
     "epi_ekf_eks_batch": (C.c_int, [C.c_void_p, C.POINTER(EkfArgs)]),

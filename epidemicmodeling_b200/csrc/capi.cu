@@ -588,6 +588,44 @@ extern "C" int epi_si_controlled_batch(epi_ctx *c, const epi_si_args *a) {
   });
 }
 
+extern "C" int epi_preprocess_batch(epi_ctx *c, const epi_preprocess_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->L < 0 || a->L > EPI_LMAX || a->n_first < 0) bad_arg("epi_preprocess_batch: bad B/L/n_first");
+    if (a->W < 1 || a->W > 32) bad_arg("epi_preprocess_batch: W must be in 1..32");
+    if (a->T < 2) bad_arg("epi_preprocess_batch: Insufficient data (T < 2)");                    // :166
+    const int Wh = (a->W + 1) / 2, nfact = (3 * (Wh - 1) > 1) ? 3 * (Wh - 1) : 1;
+    if (a->T <= nfact) bad_arg("epi_preprocess_batch: Data length must be larger than 3 times the filter order");
+    if (a->B == 0) return;
+    if (!a->cc || !a->population || (a->L > 0 && !a->ip)) bad_arg("epi_preprocess_batch: cc, population and ip are required");
+    reset_phases(c);
+    const size_t B = (size_t)a->B, T = (size_t)a->T, L = (size_t)a->L;
+    Call w(c, a->mem);
+    PreprocParams p{};
+    p.B = a->B; p.T = a->T; p.L = a->L; p.W = a->W; p.n_first = a->n_first; p.min_cases = a->min_cases;
+    p.cc = w.in(a->cc, T * B);
+    p.population = w.in(a->population, B);
+    p.ip_in = w.in(a->ip, T * L * B);
+    auto out_or_scratch = [&](double *o, size_t n) { return o ? w.out(o, n) : (double *)w.dalloc((n ? n : 1) * sizeof(double)); };
+    p.ip_out = out_or_scratch(a->ip_filled, T * L * B);
+    p.refined = out_or_scratch(a->refined, T * B);
+    p.smoothed = out_or_scratch(a->smoothed, T * B);
+    p.zerolag = out_or_scratch(a->zerolag, T * B);
+    p.normalized = out_or_scratch(a->normalized, T * B);
+    p.confirmed_norm = out_or_scratch(a->confirmed_norm, T * B);
+    p.R_v = out_or_scratch(a->R_v, T * B);
+    p.I0 = out_or_scratch(a->I0, B);
+    p.scratch = (double *)w.dalloc(2 * (T + 2 * (size_t)nfact) * B * sizeof(double));
+    PhaseScope ph(c, "preprocess");
+    launch_preprocess(p, c->stream);
+    check_launch(c, 1);
+    ph.end();
+    w.flush();
+    finish(c, a->mem);
+  });
+}
+
 extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
   return guarded(c, [&] {
     if (!a) bad_arg("null args");

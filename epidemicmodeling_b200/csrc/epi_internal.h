@@ -124,6 +124,20 @@ struct RtParams {
 };
 void launch_rt_expfit(const RtParams &p, cudaStream_t st);
 
+// per-region preprocessing (preprocess.cu).  Every per-region array is [rows][B], B = regions.
+struct PreprocParams {
+  int B, T, L, W, n_first;
+  double min_cases;
+  const double *cc;          // [T][B] cumulative confirmed cases (NaN allowed)
+  const double *population;  // [B]
+  const double *ip_in;       // [T][L][B] NPI levels (NaN allowed)
+  double *ip_out;            // [T][L][B]
+  double *refined, *smoothed, *zerolag, *normalized, *confirmed_norm, *R_v;  // [T][B]
+  double *I0;                // [B]
+  double *scratch;           // [2][T + 2*nfact][B]
+};
+void launch_preprocess(const PreprocParams &p, cudaStream_t st);
+
 struct SiParams {
   int B, K;
   double dt;

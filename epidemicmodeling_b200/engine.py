@@ -311,6 +311,30 @@ class Engine:
             self._done()
         return s, i
 
+    def preprocess(self, cc, population, ip, *, W=7, n_first=7, min_cases=1.0):
+        """Data-cleaning block of Tools/TrainPredictPrescribeNPI.m (:121-128, :162-187, :200-201, :240)
+        for B regions: cc [T,B] cumulative cases, population [B], ip [T,L,B] NPI levels (NaN allowed).
+        Returns dict(ip_filled [T,L,B]; refined, smoothed, zerolag, normalized, confirmed_norm, R_v [T,B]; I0 [B])."""
+        mem = self._mode(cc, population, ip)
+        T, B = int(cc.shape[0]), int(cc.shape[1])
+        L = int(ip.shape[1])
+        a = K.PreprocessArgs()
+        a.mem, a.B, a.T, a.L, a.W, a.n_first, a.min_cases = mem, B, T, L, int(W), int(n_first), float(min_cases)
+        a.cc = self._in(cc, mem, n=T * B)
+        a.population = self._in(population, mem, n=B)
+        a.ip = self._in(ip, mem, n=T * L * B)
+        res = {}
+        res["ip_filled"], a.ip_filled = self._out((T, L, B), mem)
+        for k in ("refined", "smoothed", "zerolag", "normalized", "confirmed_norm", "R_v"):
+            res[k], ptr = self._out((T, B), mem)
+            setattr(a, k, ptr)
+        res["I0"], a.I0 = self._out((B,), mem)
+        try:
+            self._ck(self._lib.epi_preprocess_batch(self._h, C.byref(a)))
+        finally:
+            self._done()
+        return res
+
     RT_OUTPUTS = ("S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH", "innovations", "rho")
 
     def rt_expfit(self, x, s_init, params, w_bar, Ps_init, Q, R, *, T, G=1, v_bar=0.0, beta=1.0, gamma=1.0,

@@ -201,6 +201,25 @@ typedef struct {
 } epi_si_args;
 int epi_si_controlled_batch(epi_ctx *ctx, const epi_si_args *a);
 
+/* Per-region preprocessing ------------------------------------------------------
+ * replaces the data-cleaning block of Tools/TrainPredictPrescribeNPI.m for B regions at once:
+ * :121-128 NPI forward fill (N/A -> previous day's level, else 0); :162-172 new cases =
+ * diff of the cumulative series, negatives clipped, trailing NaN = last valid value, other NaN = 0;
+ * :173 causal W-day moving average (filter(ones(1,W), W, .)); :174 zero-phase round(W/2)-tap moving
+ * average (filtfilt); :175-180 normalisation by the population and the cumulative smoothed series;
+ * :200-201 I0 = max(min_cases, mean of the first n_first positive smoothed days); :240
+ * R_v = 0.1 ((zero-phase - refined)/N)^2.  cc [T][B], population [B], ip [T][L][B]; outputs [T][B]
+ * (ip_filled [T][L][B], I0 [B]), each optional except none.  T must exceed 3 (round(W/2) - 1)
+ * (filtfilt's data-length rule) and be >= 2 (:166); 1 <= W <= 32. */
+typedef struct {
+  int mem;
+  int B, T, L, W, n_first;
+  double min_cases;
+  const double *cc, *population, *ip;
+  double *ip_filled, *refined, *smoothed, *zerolag, *normalized, *confirmed_norm, *R_v, *I0;
+} epi_preprocess_args;
+int epi_preprocess_batch(epi_ctx *ctx, const epi_preprocess_args *a);
+
 /* Exponential-fit EKF / smoother -------------------------------------------------
  * replaces  [S_MINUS, S_PLUS, P_MINUS, P_PLUS, K_GAIN, S_SMOOTH, P_SMOOTH, innovations, rho] =
  *              Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma,

@@ -1223,3 +1223,101 @@ int orc_rt_expfit_ekf(const double *x, int T, const double *s_init, const double
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Per-region preprocessing that feeds the filters              */
+/* Tools/TrainPredictPrescribeNPI.m:121-128 (NPI fill), :165-187 (case series), */
+/* :200-201 (I0), :240 (R_v)                                                   */
+/* ------------------------------------------------------------------------- */
+/* y = filter(b, 1, x, zi) for an FIR b[0..nb-1] in MATLAB's direct form II transposed:
+ *   y(n) = b1 x(n) + z1;  z_i = b_{i+1} x(n) + z_{i+1}  (i < nb-1);  z_{nb-1} = b_nb x(n).
+ * z (nb-1 values) is updated in place. */
+static void fir_df2t(const double *b, int nb, const double *x, int n, double *z, double *y) {
+  for (int t = 0; t < n; ++t) {
+    const double xt = x[t];
+    const double yt = (nb > 1) ? (b[0] * xt + z[0]) : (b[0] * xt);
+    for (int i = 0; i + 2 < nb; ++i) z[i] = b[i + 1] * xt + z[i + 1];
+    if (nb > 1) z[nb - 2] = b[nb - 1] * xt;
+    if (y) y[t] = yt;
+  }
+}
+/* MATLAB filtfilt(b, a, x) for an FIR with scalar a (normalised first, as filter does):
+ * odd reflection of nfact = 3(nb-1) samples at both ends, initial states zi * (first sample)
+ * with zi the steady state of a unit input (zi_i = sum_{j>i} b_j), forward pass, reversed pass. */
+static int fir_filtfilt(const double *b, int nb, const double *x, int n, double *y) {
+  const int nfact = (3 * (nb - 1) > 1) ? 3 * (nb - 1) : 1;
+  if (n <= nfact) return -1; /* "Data length must be larger than 3 times the filter order" */
+  const int ne = n + 2 * nfact;
+  double *xe = (double *)malloc(sizeof(double) * (size_t)ne * 2), *ye = xe + ne;
+  double zi[32], z[32];
+  for (int i = 0; i + 1 < nb; ++i) { /* zi(i) = b(i+1) + zi(i+1) solved from the last one up */
+    zi[i] = 0.0;
+  }
+  for (int i = nb - 2; i >= 0; --i) zi[i] = b[i + 1] + ((i + 1 < nb - 1) ? zi[i + 1] : 0.0);
+  for (int i = 0; i < nfact; ++i) xe[i] = 2.0 * x[0] - x[nfact - i];
+  for (int i = 0; i < n; ++i) xe[nfact + i] = x[i];
+  for (int i = 0; i < nfact; ++i) xe[nfact + n + i] = 2.0 * x[n - 1] - x[n - 2 - i];
+  for (int i = 0; i + 1 < nb; ++i) z[i] = zi[i] * xe[0];
+  fir_df2t(b, nb, xe, ne, z, ye);
+  for (int i = 0; i < ne / 2; ++i) { double t = ye[i]; ye[i] = ye[ne - 1 - i]; ye[ne - 1 - i] = t; }
+  for (int i = 0; i + 1 < nb; ++i) z[i] = zi[i] * ye[0];
+  fir_df2t(b, nb, ye, ne, z, xe);
+  for (int i = 0; i < n; ++i) y[i] = xe[ne - 1 - nfact - i];
+  free(xe);
+  return 0;
+}
+
+/* One region.  cc[T] cumulative confirmed cases (NaN allowed), ip[T][L] NPI levels (NaN allowed,
+ * filled in place), population N, W = SmoothingWinLen.  Outputs [T] each: refined, smoothed,
+ * zerolag, normalized (= smoothed/N), confirmed_norm (= cumsum(smoothed)/N), R_v; *I0.
+ * Returns 0, -1 if T < 2 (:166 "Insufficient data"), -2 if T <= 3*(round(W/2)-1) (filtfilt). */
+int orc_preprocess_region(const double *cc, int T, double N, int W, int n_first, double min_cases, double *ip,
+                          int L, double *refined, double *smoothed, double *zerolag, double *normalized,
+                          double *confirmed_norm, double *R_v, double *I0) {
+  if (T < 2) return -1;
+  /* :121-128 */
+  for (int j = 0; j < L; ++j)
+    for (int i = 1; i < T; ++i)
+      if (ip[i * L + j] != ip[i * L + j] && !(ip[(i - 1) * L + j] != ip[(i - 1) * L + j])) ip[i * L + j] = ip[(i - 1) * L + j];
+  for (int q = 0; q < T * L; ++q)
+    if (ip[q] != ip[q]) ip[q] = 0.0;
+  /* :162-172 */
+  for (int t = 0; t < T; ++t) {
+    double d = cc[t] - cc[t > 0 ? t - 1 : 0]; /* diff([cc(1); cc]) */
+    if (d < 0.0) d = 0.0;
+    refined[t] = d;
+  }
+  if (refined[T - 1] != refined[T - 1]) {
+    int last = -1;
+    for (int t = T - 1; t >= 0; --t)
+      if (!(refined[t] != refined[t])) { last = t; break; }
+    if (last >= 0) refined[T - 1] = refined[last];
+  }
+  for (int t = 0; t < T; ++t)
+    if (refined[t] != refined[t]) refined[t] = 0.0;
+  /* :173 causal moving average */
+  double b[32], z[32];
+  for (int i = 0; i < W; ++i) { b[i] = 1.0 / (double)W; z[i] = 0.0; }
+  fir_df2t(b, W, refined, T, z, smoothed);
+  /* :174 zero-phase moving average of round(W/2) taps */
+  const int Wh = (int)floor((double)W / 2.0 + 0.5);
+  for (int i = 0; i < Wh; ++i) b[i] = 1.0 / (double)Wh;
+  if (fir_filtfilt(b, Wh, refined, T, zerolag)) return -2;
+  /* :175-180, :240 */
+  double cs = 0.0;
+  for (int t = 0; t < T; ++t) {
+    normalized[t] = smoothed[t] / N;
+    cs += smoothed[t];
+    confirmed_norm[t] = cs / N;
+    const double e = (zerolag[t] - refined[t]) / N;
+    R_v[t] = 0.1 * (e * e);
+  }
+  /* :200-201 */
+  double acc = 0.0;
+  int cnt = 0;
+  for (int t = 0; t < T && cnt < n_first; ++t)
+    if (smoothed[t] > 0.0) { acc += smoothed[t]; ++cnt; }
+  const double mean = cnt ? acc / (double)cnt : NAN; /* mean([]) = NaN */
+  *I0 = mmax(min_cases, mean);
+  return 0;
+}

@@ -110,6 +110,11 @@ int orc_rt_expfit_ekf(const double *x, int T, const double *s_init, const double
                       int W, int order, double *S_MINUS, double *S_PLUS, double *P_MINUS, double *P_PLUS,
                       double *K_GAIN, double *S_SMOOTH, double *P_SMOOTH, double *innovations, double *rho);
 
+/* per-region preprocessing: Tools/TrainPredictPrescribeNPI.m:121-128, 162-187, 200-201, 240 */
+int orc_preprocess_region(const double *cc, int T, double N, int W, int n_first, double min_cases, double *ip,
+                          int L, double *refined, double *smoothed, double *zerolag, double *normalized,
+                          double *confirmed_norm, double *R_v, double *I0);
+
 /* random NPI schedules (TrainPredictPrescribeNPI.m:499-510) on a Philox4x32-10 counter stream */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_random_schedule(uint64_t seed, uint32_t region, uint32_t scenario, int n_scenarios, int L, int K,

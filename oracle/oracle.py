@@ -209,6 +209,25 @@ def Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma
             o["innovations"].reshape(1, T), o["rho"].reshape(T))
 
 
+def preprocess_region(cc, ip, N, W=7, n_first=7, min_cases=1.0):
+    """TrainPredictPrescribeNPI.m:121-128,162-187,200-201,240 for one region.  cc [T], ip [T, L].
+    Returns dict(refined, smoothed, zerolag, normalized, confirmed_norm, R_v [T]; ip [T, L]; I0)."""
+    cc = _f(cc).ravel()
+    T = cc.size
+    ip = np.array(ip, dtype=np.float64, order="C").reshape(T, -1).copy()
+    o = {k: np.zeros(T) for k in ("refined", "smoothed", "zerolag", "normalized", "confirmed_norm", "R_v")}
+    I0 = C.c_double()
+    lib().orc_preprocess_region.restype = C.c_int
+    rc = lib().orc_preprocess_region(_p(cc), C.c_int(T), C.c_double(float(N)), C.c_int(int(W)), C.c_int(int(n_first)),
+                                     C.c_double(float(min_cases)), _p(ip), C.c_int(ip.shape[1]),
+                                     *[_p(o[k]) for k in ("refined", "smoothed", "zerolag", "normalized",
+                                                          "confirmed_norm", "R_v")], C.byref(I0))
+    if rc:
+        raise ValueError("Insufficient data" if rc == -1 else "Data length must be larger than 3 times the filter order")
+    o["ip"], o["I0"] = ip, I0.value
+    return o
+
+
 def pareto(J0, J1):
     J0, J1 = _f(J0).ravel(), _f(J1).ravel()
     n = J0.size

@@ -19,7 +19,8 @@ from epidemicmodeling_b200.engine import pack_params
 
 pytestmark = pytest.mark.gpu
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
 EKF_KEYS = ("u_opt", "u_opt_smooth", "S_MINUS", "S_PLUS", "S_SMOOTH", "P_MINUS", "P_PLUS", "P_SMOOTH",
             "K_GAIN", "innovations", "rho")
 TOL_STATE = 1e-9   # north_star tolerance for SEIRP / EKF states
@@ -415,6 +416,69 @@ def test_generated_schedules_match_oracle_and_supplied(engine, nS):
     bad = pack_params([dict(d, u_min=np.full(L, np.nan)) for d in prm_d], L)
     with pytest.raises(K.EpiError):
         engine.rollout_cost(bad, x0, None, Kn, L, B=B, seed=seed, **kw)            # level bounds are required
+
+
+# ------------------------------------------------------------------------------ preprocessing + CSV pipeline
+def test_preprocess_batch_bit_exact(engine):
+    rng = np.random.default_rng(8)
+    T, B, L = 97, 70, 12
+    nc = np.maximum(0, rng.poisson(40, (T, B)) + np.arange(T)[:, None] * rng.random(B))
+    cc = np.cumsum(nc, axis=0)
+    cc[rng.integers(1, T, 200), rng.integers(0, B, 200)] = np.nan
+    cc[T - 1, ::5] = np.nan
+    cc[40, 3] -= 500.0
+    cc[:, 7] = 0.0                                       # a region without cases: I0 = min_cases
+    cc[:, 9] = np.nan                                    # a region without data at all
+    ip = rng.integers(0, 5, (T, L, B)).astype(float)
+    ip[rng.integers(0, T, 900), rng.integers(0, L, 900), rng.integers(0, B, 900)] = np.nan
+    pop = rng.uniform(1e5, 3e8, B)
+    got = engine.preprocess(cc, pop, ip)
+    o = orc()
+    for b in range(B):
+        ref = o.preprocess_region(cc[:, b], ip[:, :, b], pop[b])
+        for k in ("refined", "smoothed", "zerolag", "normalized", "confirmed_norm", "R_v"):
+            assert_bits(got[k][:, b], ref[k], f"{k} region {b}")
+        assert_bits(got["ip_filled"][:, :, b], ref["ip"], f"ip region {b}")
+        assert_bits(got["I0"][b:b + 1], np.array([ref["I0"]]), f"I0 region {b}")
+    with pytest.raises(K.EpiError):
+        engine.preprocess(cc[:9], pop, ip[:9])          # filtfilt's data-length rule
+
+
+def test_csv_to_prescriptions_pipeline(engine, tmp_path):
+    """OxCGRT-format CSV -> preprocess -> 3-state EKF/EKS -> optimal-NPI sweep -> knee -> prescription
+    CSV, every numeric stage on the device; J0/J1 against the oracle on the same preprocessed inputs."""
+    import importlib.util
+    import pandas as pd
+    from epidemicmodeling_b200 import pipeline, xprize_io as xio
+    spec = importlib.util.spec_from_file_location("pfc", os.path.join(os.path.dirname(HERE), "tools", "prescribe_from_csv.py"))
+    pfc = importlib.util.module_from_spec(spec); spec.loader.exec_module(pfc)
+    data, out = str(tmp_path / "ox.csv"), str(tmp_path / "presc.csv")
+    regions, start, end = pfc.synthetic_oxcgrt(data, 3, 60)
+    eps = syn.epsilon_grid_xprize02(10)
+    Tf = 20
+    res = pipeline.prescribe_from_csv(engine, data, start, end, Tf, eps, regions, out_file=out,
+                                      forecast_dates=[f"2020-06-{d + 1:02d}" for d in range(Tf)])
+    assert res["J0"].shape == (3, 10) and res["u_knee"].shape == (3, Tf, 12)
+    assert np.isfinite(res["J0"]).all() and np.isfinite(res["J1"]).all()
+    df = pd.read_csv(out, keep_default_na=False)
+    assert list(df.columns)[:4] == ["PrescriptionIndex", "CountryName", "RegionName", "Date"] and len(df) == 3 * Tf
+    lv = df[xio.NPI_COLUMNS].to_numpy()
+    assert (lv >= 0).all() and (lv <= xio.NPI_MAXES[None, :]).all()
+    assert not lv[Tf - 1::Tf].any()                      # u_opt_smooth(:, T) = 0 quirk reaches the file
+    # oracle on the same (device-preprocessed) inputs
+    o = orc()
+    pre, ids = res["pre"], res["ids"]
+    inputs = [pipeline.setup_from_preprocessed(pre, b, regions[g]["N"], regions[g]["a"], regions[g]["b"], xio.NPI_MAXES,
+                                               regions[g]["weights"], 60, Tf) for b, g in enumerate(ids)]
+    S = wl.run_fixed_input(engine, inputs)
+    for r, rin in enumerate(inputs):
+        s6, Th, Sr = rin["setup6"], rin["T_hist"], S[:, :, r].T
+        reg = o.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"], s6["Ps_init"],
+                            s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21, Sr[0, Th - 1], Sr[1, Th - 1],
+                            Sr[2, Th - 1], (Sr[0, :Th] * Sr[1, :Th]) * Sr[2, :Th], rin["weights"])
+        j0, j1, m, io, _ = o.sweep_region(reg, eps)
+        assert_bits(res["J0"][r], j0, "pipeline J0"); assert_bits(res["J1"][r], j1, "pipeline J1")
+        assert res["I_opt"][r] == io
 
 
 # ------------------------------------------------------------------------------ Rt_ExpFitEKF

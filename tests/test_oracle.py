@@ -14,7 +14,13 @@ import cases
 from oracle import numpy_twin as tw
 from oracle import oracle as orc
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def assert_bits(a, b, what=""):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64)), what
 EKF_KEYS = ("u_opt", "u_opt_smooth", "S_MINUS", "S_PLUS", "S_SMOOTH", "P_MINUS", "P_PLUS", "P_SMOOTH",
             "K_GAIN", "innovations", "rho")
 
@@ -430,3 +436,61 @@ def test_rt_expfit_second_order_terms_and_order_check():
     assert 1e-9 < d[0] < 1e-1 and 1e-9 < d[1] < 1e-1      # the Hessian terms act, as a small correction
     with pytest.raises(ValueError, match="Undefined order"):
         orc.Rt_ExpFitEKF(**dict(c1, order=3))
+
+
+# ---------------------------------------------------------------------------- preprocessing + wire formats
+def test_preprocess_oracle_against_scipy_and_rules():
+    """TrainPredictPrescribeNPI.m:121-128,162-187,200-201,240.  MATLAB's filter / filtfilt semantics
+    are those of scipy.signal.lfilter / filtfilt(padtype='odd', padlen=3*(ntaps-1))."""
+    from scipy import signal
+    rng = np.random.default_rng(1)
+    T = 140
+    nc = np.maximum(0, rng.poisson(50, T) + np.arange(T) * 2.0)
+    cc = np.cumsum(nc).astype(float)
+    cc[30] -= 400.0                         # a downward correction: negative diff -> 0, next diff inflated
+    cc[50] = np.nan                         # a gap: two NaN diffs -> 0
+    cc[-1] = np.nan                         # missing last day -> previous valid value
+    ip = rng.integers(0, 4, (T, 12)).astype(float)
+    ip[10:15, 3] = np.nan; ip[0, 5] = np.nan; ip[0:3, 7] = np.nan
+    N = 2.5e6
+    r = orc.preprocess_region(cc, ip, N)
+    ref = r["refined"]
+    assert ref[0] == 0 and ref[30] == 0 and ref[50] == 0 and ref[51] == 0 and ref[-1] == ref[-2] and (ref >= 0).all()
+    assert np.allclose(r["smoothed"], signal.lfilter(np.ones(7) / 7, 1, ref), rtol=0, atol=1e-12 * ref.max())
+    assert np.allclose(r["zerolag"], signal.filtfilt(np.ones(4) / 4, 1, ref, padtype="odd", padlen=9), rtol=0,
+                       atol=1e-12 * ref.max())
+    assert_bits(r["normalized"], r["smoothed"] / N)
+    assert np.allclose(r["confirmed_norm"], np.cumsum(r["smoothed"]) / N, rtol=1e-14)
+    assert_bits(r["R_v"], 0.1 * ((r["zerolag"] - ref) / N) ** 2)
+    first = r["smoothed"][r["smoothed"] > 0][:7]
+    assert r["I0"] == max(1.0, first.sum() / first.size)
+    assert (r["ip"][10:15, 3] == ip[9, 3]).all() and r["ip"][0, 5] == 0 and (r["ip"][0:3, 7] == 0).all()
+    assert not np.isnan(r["ip"]).any()
+    with pytest.raises(ValueError, match="Data length"):
+        orc.preprocess_region(cc[:9], ip[:9], N)
+    assert orc.preprocess_region(np.zeros(20), np.zeros((20, 12)), N)["I0"] == 1.0   # mean([]) = NaN -> min_cases
+
+
+def test_xprize_wire_formats_round_trip(tmp_path):
+    """read_oxcgrt on a file in the Oxford format, write_prescriptions in the format of
+    xprize-sample-data/*_prescriptions_example.csv (header checked literally)."""
+    import importlib.util
+    import pandas as pd
+    from epidemicmodeling_b200 import xprize_io as xio
+    spec = importlib.util.spec_from_file_location("pfc", os.path.join(ROOT, "tools", "prescribe_from_csv.py"))
+    pfc = importlib.util.module_from_spec(spec); spec.loader.exec_module(pfc)
+    data = str(tmp_path / "ox.csv")
+    regions, start, end = pfc.synthetic_oxcgrt(data, 4, 40)
+    ids, dates, cc, dd, ip = xio.read_oxcgrt(data, start, end)
+    assert ids == list(regions) and cc.shape == (40, 4) and ip.shape == (40, 12, 4) and dates[0] == 20200315
+    assert np.isnan(cc).sum() >= 4 and np.isnan(ip).sum() >= 4 and np.isnan(dd).all()
+    sub = xio.read_oxcgrt(data, "2020-03-20", "2020-03-29", geo_ids={ids[1]})
+    assert sub[0] == [ids[1]] and sub[2].shape == (10, 1) and np.array_equal(sub[2][:, 0], cc[5:15, 1], equal_nan=True)
+    out = str(tmp_path / "presc.csv")
+    sch = np.arange(4 * 3 * 12).reshape(4, 3, 12) % 4
+    xio.write_prescriptions(out, ids, ["2020-08-01", "2020-08-02", "2020-08-03"], [sch, sch])
+    df = pd.read_csv(out, keep_default_na=False)
+    assert list(df.columns) == ["PrescriptionIndex", "CountryName", "RegionName", "Date"] + xio.NPI_COLUMNS
+    assert len(df) == 2 * 4 * 3 and set(df["PrescriptionIndex"]) == {0, 1} and (df["RegionName"] == "").all()
+    assert (df["CountryName"] + " " == pd.Series([i for _ in range(2) for i in ids for _ in range(3)])).all()
+    assert np.array_equal(df[xio.NPI_COLUMNS].to_numpy()[:12], sch.reshape(12, 12))
