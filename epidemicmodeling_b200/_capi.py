@@ -71,6 +71,11 @@ class PreprocessArgs(C.Structure):
                 ("confirmed_norm", _dp), ("R_v", _dp), ("I0", _dp)]
 
 
+class NnlsArgs(C.Structure):
+    _fields_ = [("mem", C.c_int), ("B", C.c_int), ("n", C.c_int), ("p", C.c_int), ("max_alt", C.c_int),
+                ("X", _dp), ("y", _dp), ("a", _dp), ("b", _dp), ("n_alt", _dp)]
+
+
 class NpiCostArgs(C.Structure):
     _fields_ = [("mem", C.c_int), ("B", C.c_int), ("T", C.c_int), ("L", C.c_int), ("G", C.c_int),
                 ("newcases", _dp), ("inputs", _dp), ("weights", _dp), ("J0", _dp), ("J1", _dp)]
@@ -126,6 +131,7 @@ SYMBOLS = {
     "epi_random_schedules": (C.c_int, [C.c_void_p, C.POINTER(SchedulesArgs)]),
     "epi_rt_expfit_batch": (C.c_int, [C.c_void_p, C.POINTER(RtExpFitArgs)]),
     "epi_preprocess_batch": (C.c_int, [C.c_void_p, C.POINTER(PreprocessArgs)]),
+    "epi_nnls_affine_batch": (C.c_int, [C.c_void_p, C.POINTER(NnlsArgs)]),
     "epi_npicost_batch": (C.c_int, [C.c_void_p, C.POINTER(NpiCostArgs)]),
     "epi_si_controlled_batch": (C.c_int, [C.c_void_p, C.POINTER(SiArgs)]),
     "epi_ekf_eks_batch": (C.c_int, [C.c_void_p, C.POINTER(EkfArgs)]),

@@ -626,6 +626,33 @@ extern "C" int epi_preprocess_batch(epi_ctx *c, const epi_preprocess_args *a) {
   });
 }
 
+extern "C" int epi_nnls_affine_batch(epi_ctx *c, const epi_nnls_args *a) {
+  return guarded(c, [&] {
+    if (!a) bad_arg("null args");
+    check_mem(a->mem);
+    if (a->B < 0 || a->n < 1 || a->max_alt < 0) bad_arg("epi_nnls_affine_batch: bad B/n/max_alt");
+    if (a->p < 1 || a->p > EPI_LMAX) bad_arg("epi_nnls_affine_batch: p must be in 1..12");
+    if (a->B == 0) return;
+    if (!a->X || !a->y || !a->a || !a->b) bad_arg("epi_nnls_affine_batch: X, y, a and b are required");
+    reset_phases(c);
+    const size_t B = (size_t)a->B;
+    Call w(c, a->mem);
+    NnlsParams q{};
+    q.B = a->B; q.n = a->n; q.p = a->p; q.max_alt = a->max_alt;
+    q.X = w.in(a->X, (size_t)a->n * a->p * B);
+    q.y = w.in(a->y, (size_t)a->n * B);
+    q.a = w.out(a->a, (size_t)a->p * B);
+    q.b = w.out(a->b, B);
+    q.n_alt = w.out(a->n_alt, B);
+    PhaseScope ph(c, "nnls_affine");
+    launch_nnls_affine(q, c->stream);
+    check_launch(c, 1);
+    ph.end();
+    w.flush();
+    finish(c, a->mem);
+  });
+}
+
 extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
   return guarded(c, [&] {
     if (!a) bad_arg("null args");

@@ -138,6 +138,17 @@ struct PreprocParams {
 };
 void launch_preprocess(const PreprocParams &p, cudaStream_t st);
 
+// non-negative regression with alternating intercept (nnls.cu); every array [rows][B]
+struct NnlsParams {
+  int B, n, p, max_alt;
+  const double *X;   // [n][p][B]
+  const double *y;   // [n][B]
+  double *a;         // [p][B]
+  double *b;         // [B]
+  int *n_alt;        // [B] accepted alternations, or null
+};
+void launch_nnls_affine(const NnlsParams &q, cudaStream_t st);
+
 struct SiParams {
   int B, K;
   double dt;

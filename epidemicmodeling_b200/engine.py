@@ -335,6 +335,24 @@ class Engine:
             self._done()
         return res
 
+    def nnls_affine(self, X, y, max_alt=100):
+        """lsqnonneg + alternating intercept of TrainPredictPrescribeNPI.m:264-278 for B regions:
+        X [n,p,B], y [n,B] -> a [p,B] >= 0, b [B], n_alt [B]."""
+        mem = self._mode(X, y)
+        n, p, B = int(X.shape[0]), int(X.shape[1]), int(X.shape[2])
+        q = K.NnlsArgs()
+        q.mem, q.B, q.n, q.p, q.max_alt = mem, B, n, p, int(max_alt)
+        q.X = self._in(X, mem, n=n * p * B)
+        q.y = self._in(y, mem, n=n * B)
+        a, q.a = self._out((p, B), mem)
+        b, q.b = self._out((B,), mem)
+        k, q.n_alt = self._out((B,), mem, dtype=np.int32)
+        try:
+            self._ck(self._lib.epi_nnls_affine_batch(self._h, C.byref(q)))
+        finally:
+            self._done()
+        return a, b, k
+
     RT_OUTPUTS = ("S_MINUS", "S_PLUS", "P_MINUS", "P_PLUS", "K_GAIN", "S_SMOOTH", "P_SMOOTH", "innovations", "rho")
 
     def rt_expfit(self, x, s_init, params, w_bar, Ps_init, Q, R, *, T, G=1, v_bar=0.0, beta=1.0, gamma=1.0,

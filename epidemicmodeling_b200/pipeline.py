@@ -37,12 +37,39 @@ def setup_from_preprocessed(pre, b, N, a, bb, npi_max, weights_row, T_hist, T_fo
     T = T_hist + T_fore
     x = np.concatenate([pre["normalized"][:T_hist, b], np.full(T_fore, np.nan)])
     Rv = pre["R_v"][:T_hist, b] + 1e-30
-    R = np.concatenate([Rv, np.full(T_fore, Rv[-1])])
+    R = np.concatenate([Rv, np.full(T_fore, Rv.mean())])                         # :357 horizon = mean(R_v)
     u_hist = np.ascontiguousarray(pre["ip_filled"][:T_hist, :, b].T)            # L x T_hist
     u_fixed = np.concatenate([u_hist, np.repeat(u_hist[:, -1:], T_fore, axis=1)], axis=1)
     weights = np.repeat(np.asarray(weights_row, dtype=np.float64)[:, None], T, axis=1)
     return dict(T=T, T_hist=T_hist, u_hist=u_hist, u_fixed=u_fixed, x=x, R_v=R, setup3=setup3, setup6=setup6,
                 weights=weights)
+
+
+def train_regions(engine, pre, pops, npi_max, T_hist, n_regression_days, max_alt=100):
+    """Rounds 1-5 of the driver for every region at once (NONNEGATIVELS branch):
+    :247 3-state EKF/EKS with zero inputs  ->  :250-251,264-278 regress the smoothed alpha on
+    (NPI_MAXES - InterventionPlans) over the last n_regression_days  ->  :291-302 EKF/EKS with the
+    real inputs and the fitted (a, b)  ->  :305-306,326-339 second regression.  Returns dict(a1, b1, a2, b2)."""
+    B = pre["I0"].shape[0]
+    zeros12 = np.zeros(npi_max.size)
+
+    def smoothed_alpha(a, b, real_inputs):
+        inputs = [setup_from_preprocessed(pre, r, float(pops[r]), a[:, r], float(b[r]), npi_max, zeros12, T_hist, 0)
+                  for r in range(B)]
+        if not real_inputs:
+            for rin in inputs:
+                rin["u_fixed"] = np.zeros_like(rin["u_fixed"])        # :203 the first round assumes zero inputs
+        return wl.run_fixed_input(engine, inputs)[:, 2, :]             # S_SMOOTH(3, :) per region  [T, B]
+
+    n = int(n_regression_days)
+    X = np.ascontiguousarray(npi_max[None, :, None] - pre["ip_filled"][T_hist - n:T_hist])   # [n, L, B]
+    out = {}
+    a, b = np.zeros((npi_max.size, B)), np.zeros(B)
+    for rnd, real in ((1, False), (2, True)):
+        y = np.ascontiguousarray(smoothed_alpha(a, b, real)[T_hist - n:T_hist])
+        a, b, k = engine.nnls_affine(X, y, max_alt=max_alt)
+        out[f"a{rnd}"], out[f"b{rnd}"], out[f"alt{rnd}"] = a, b, k
+    return out
 
 
 def prescribe_from_csv(engine, data_file, start_date, end_date, T_fore, eps, regions, out_file=None,

@@ -220,6 +220,21 @@ typedef struct {
 } epi_preprocess_args;
 int epi_preprocess_batch(epi_ctx *ctx, const epi_preprocess_args *a);
 
+/* Non-negative regression between the EKF rounds ---------------------------------
+ * replaces  reg_coef_a = lsqnonneg(X, y)  followed by the alternating-intercept loop of
+ * Tools/TrainPredictPrescribeNPI.m:264-278 (and :326-339) for B regions at once: X [n][p][B]
+ * (n regression days, p <= 12 NPIs: NPI_MAXES - InterventionPlans), y [n][B] (the smoothed alpha);
+ * a [p][B] >= 0, b [B], n_alt [B] (accepted alternations, optional).  max_alt = 100 in the reference
+ * (NONNEGATIVELS_IRERATIONS); 0 = plain lsqnonneg with b = 0. */
+typedef struct {
+  int mem;
+  int B, n, p, max_alt;
+  const double *X, *y;
+  double *a, *b;
+  int *n_alt;
+} epi_nnls_args;
+int epi_nnls_affine_batch(epi_ctx *ctx, const epi_nnls_args *a);
+
 /* Exponential-fit EKF / smoother -------------------------------------------------
  * replaces  [S_MINUS, S_PLUS, P_MINUS, P_PLUS, K_GAIN, S_SMOOTH, P_SMOOTH, innovations, rho] =
  *              Rt_ExpFitEKF(x, s_init, params, w_bar, v_bar, Ps_init, Q_w, R_v, beta, gamma,

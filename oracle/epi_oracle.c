@@ -1321,3 +1321,150 @@ int orc_preprocess_region(const double *cc, int T, double N, int W, int n_first,
   *I0 = mmax(min_cases, mean);
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Non-negative regression between the EKF rounds               */
+/* Tools/TrainPredictPrescribeNPI.m:264-278 (and :326-339): lsqnonneg +       */
+/* alternating intercept                                                       */
+/* ------------------------------------------------------------------------- */
+#define NNLS_PMAX 12
+/* Least squares on the passive set through the normal equations G_PP z_P = c_P (Cholesky in
+ * ascending index order; a non-positive pivot drops that variable: z = 0).  MATLAB solves
+ * C(:,P)\d by QR; the normal equations are this oracle's DEFINITION. */
+static void nnls_solve_passive(const double G[NNLS_PMAX][NNLS_PMAX], const double *c, const int *P, int p, double *z) {
+  int idx[NNLS_PMAX], m = 0;
+  double Lc[NNLS_PMAX][NNLS_PMAX], yv[NNLS_PMAX];
+  int dead[NNLS_PMAX];
+  for (int j = 0; j < p; ++j) { z[j] = 0.0; if (P[j]) idx[m++] = j; }
+  for (int i = 0; i < m; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double acc = G[idx[i]][idx[j]];
+      for (int k = 0; k < j; ++k) acc = fma(-Lc[i][k], Lc[j][k], acc);
+      if (j < i) {
+        Lc[i][j] = dead[j] ? 0.0 : acc / Lc[j][j];
+      } else {
+        dead[i] = !(acc > 0.0);
+        Lc[i][i] = dead[i] ? 1.0 : sqrt(acc);
+      }
+    }
+    if (dead[i]) for (int j = 0; j < i; ++j) Lc[i][j] = 0.0;
+  }
+  for (int i = 0; i < m; ++i) { /* L y = c */
+    double acc = c[idx[i]];
+    for (int k = 0; k < i; ++k) acc = fma(-Lc[i][k], yv[k], acc);
+    yv[i] = dead[i] ? 0.0 : acc / Lc[i][i];
+  }
+  for (int i = m - 1; i >= 0; --i) { /* L' z = y */
+    double acc = yv[i];
+    for (int k = i + 1; k < m; ++k) acc = fma(-Lc[k][i], z[idx[k]], acc);
+    z[idx[i]] = dead[i] ? 0.0 : acc / Lc[i][i];
+  }
+}
+/* lsqnonneg (Lawson & Hanson 1974, ch. 23, as MATLAB's lsqnonneg.m implements it) on the moments
+ * G = C'C and c = C'd:  w = C'(d - Cx) = c - Gx. */
+static void nnls_moments(const double G[NNLS_PMAX][NNLS_PMAX], const double *c, double tol, int p, double *x) {
+  int P[NNLS_PMAX], Z[NNLS_PMAX];
+  double w[NNLS_PMAX], z[NNLS_PMAX];
+  for (int j = 0; j < p; ++j) { P[j] = 0; Z[j] = 1; x[j] = 0.0; w[j] = c[j]; }
+  const int itmax = 3 * p;
+  int iter = 0;
+  for (;;) {
+    int anyZ = 0, t = -1;
+    double best = 0.0;
+    for (int j = 0; j < p; ++j)
+      if (Z[j]) {
+        anyZ = 1;
+        if (w[j] > tol && (t < 0 || w[j] > best)) { best = w[j]; t = j; } /* first maximum among w(Z) */
+      }
+    if (!anyZ || t < 0) break;
+    /* t = argmax over ALL of Z (MATLAB: [~,t] = max(wz)); the test above is any(w(Z) > tol) */
+    t = -1;
+    for (int j = 0; j < p; ++j)
+      if (Z[j] && (t < 0 || w[j] > best)) { best = w[j]; t = j; }
+    P[t] = 1; Z[t] = 0;
+    nnls_solve_passive(G, c, P, p, z);
+    int stop = 0;
+    for (;;) {
+      int neg = 0;
+      for (int j = 0; j < p; ++j) if (P[j] && z[j] <= 0.0) neg = 1;
+      if (!neg) break;
+      if (++iter > itmax) { stop = 1; break; } /* lsqnonneg.m: exitflag 0, x = z */
+      double alpha = INFINITY;
+      for (int j = 0; j < p; ++j)
+        if (P[j] && z[j] <= 0.0) { const double a = x[j] / (x[j] - z[j]); if (a < alpha) alpha = a; }
+      for (int j = 0; j < p; ++j) x[j] = x[j] + alpha * (z[j] - x[j]);
+      for (int j = 0; j < p; ++j) { Z[j] = (fabs(x[j]) < tol && P[j]) || Z[j]; P[j] = !Z[j]; }
+      nnls_solve_passive(G, c, P, p, z);
+    }
+    for (int j = 0; j < p; ++j) x[j] = z[j];
+    if (stop) break;
+    for (int j = 0; j < p; ++j) { /* w = c - G x */
+      double acc = c[j];
+      for (int l = 0; l < p; ++l) acc = fma(-G[j][l], x[l], acc);
+      w[j] = acc;
+    }
+  }
+}
+/* X [n][p] row-major, y [n]  ->  a [p] >= 0, b, number of accepted alternations.
+ * :264 a = lsqnonneg(X, y), b = 0; then up to 100 rounds of  a' = lsqnonneg(X, y - b),
+ * b' = mean(y - X a) and err' = sum((y - X a - b').^2) -- both with the OLD a, as written --
+ * accepted while err' < err (:267-277). */
+int orc_nnls_affine(const double *X, const double *y, int n, int p, int max_alt, double *a, double *b_out) {
+  double G[NNLS_PMAX][NNLS_PMAX], Xty[NNLS_PMAX], Xt1[NNLS_PMAX], cs[NNLS_PMAX], c[NNLS_PMAX] = {0}, at[NNLS_PMAX];
+  for (int j = 0; j < p; ++j) {
+    double sy = 0.0, s1 = 0.0, sa = 0.0;
+    for (int i = 0; i < n; ++i) { sy = fma(X[i * p + j], y[i], sy); s1 += X[i * p + j]; sa += fabs(X[i * p + j]); }
+    Xty[j] = sy; Xt1[j] = s1; cs[j] = sa;
+    for (int l = 0; l <= j; ++l) {
+      double g = 0.0;
+      for (int i = 0; i < n; ++i) g = fma(X[i * p + j], X[i * p + l], g);
+      G[j][l] = g; G[l][j] = g;
+    }
+  }
+  double norm1 = 0.0;
+  for (int j = 0; j < p; ++j) norm1 = mmax(norm1, cs[j]);
+  const double tol = ((10.0 * 2.220446049250313e-16) * norm1) * (double)(n > p ? n : p); /* lsqnonneg.m default TolX */
+  double b = 0.0;
+  for (int j = 0; j < p; ++j) c[j] = Xty[j];
+  nnls_moments(G, c, tol, p, a);
+  double min_err = 0.0;
+  for (int i = 0; i < n; ++i) {
+    double xa = X[i * p] * a[0];
+    for (int j = 1; j < p; ++j) xa = fma(X[i * p + j], a[j], xa);
+    const double r = y[i] - xa;
+    min_err += r * r;
+  }
+  int k = 0;
+  for (; k < max_alt; ++k) {
+    for (int j = 0; j < p; ++j) c[j] = Xty[j] - b * Xt1[j];   /* X'(y - b) */
+    nnls_moments(G, c, tol, p, at);
+    double sm = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double xa = X[i * p] * a[0];
+      for (int j = 1; j < p; ++j) xa = fma(X[i * p + j], a[j], xa);
+      sm += y[i] - xa;
+    }
+    const double b_t = sm / (double)n;
+    double err = 0.0;
+    for (int i = 0; i < n; ++i) {
+      double xa = X[i * p] * a[0];
+      for (int j = 1; j < p; ++j) xa = fma(X[i * p + j], a[j], xa);
+      const double r = (y[i] - xa) - b_t;
+      err += r * r;
+    }
+    if (err < min_err) {
+      for (int j = 0; j < p; ++j) a[j] = at[j];
+      b = b_t; min_err = err;
+    } else {
+      break;
+    }
+  }
+  *b_out = b;
+  return k;
+}
+/* plain lsqnonneg for the tests */
+void orc_lsqnonneg(const double *X, const double *y, int n, int p, double *a) {
+  double dummy;
+  /* max_alt = 0: only the first call of orc_nnls_affine */
+  orc_nnls_affine(X, y, n, p, 0, a, &dummy);
+}

@@ -115,6 +115,10 @@ int orc_preprocess_region(const double *cc, int T, double N, int W, int n_first,
                           int L, double *refined, double *smoothed, double *zerolag, double *normalized,
                           double *confirmed_norm, double *R_v, double *I0);
 
+/* non-negative regression with alternating intercept: TrainPredictPrescribeNPI.m:264-278 */
+int orc_nnls_affine(const double *X, const double *y, int n, int p, int max_alt, double *a, double *b);
+void orc_lsqnonneg(const double *X, const double *y, int n, int p, double *a);
+
 /* random NPI schedules (TrainPredictPrescribeNPI.m:499-510) on a Philox4x32-10 counter stream */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void orc_random_schedule(uint64_t seed, uint32_t region, uint32_t scenario, int n_scenarios, int L, int K,

@@ -228,6 +228,22 @@ def preprocess_region(cc, ip, N, W=7, n_first=7, min_cases=1.0):
     return o
 
 
+def lsqnonneg(X, y):
+    X = np.ascontiguousarray(X, dtype=np.float64); y = _f(y).ravel()
+    a = np.zeros(X.shape[1])
+    lib().orc_lsqnonneg(_p(X), _p(y), C.c_int(X.shape[0]), C.c_int(X.shape[1]), _p(a))
+    return a
+
+
+def nnls_affine(X, y, max_alt=100):
+    """TrainPredictPrescribeNPI.m:264-278: (a >= 0, b, accepted alternations)."""
+    X = np.ascontiguousarray(X, dtype=np.float64); y = _f(y).ravel()
+    a = np.zeros(X.shape[1]); b = C.c_double()
+    lib().orc_nnls_affine.restype = C.c_int
+    k = lib().orc_nnls_affine(_p(X), _p(y), C.c_int(X.shape[0]), C.c_int(X.shape[1]), C.c_int(int(max_alt)), _p(a), C.byref(b))
+    return a, b.value, k
+
+
 def pareto(J0, J1):
     J0, J1 = _f(J0).ravel(), _f(J1).ravel()
     n = J0.size

