@@ -35,8 +35,8 @@ FLOPS_EKF_EKS_M6 = 4758.0
 BYTES_FUSED_M6 = 864.0            # packed tape written once + read once
 KERNEL_ALGO = {                   # per trajectory-day: (algorithmic bytes, canonical flops)
     "ekf_forward": (432.0, 2314.0),   # tape write (S-, S+, packed P-, P+)
-    "eks_gain": (432.0, 1310.0),      # tape read; P+A' + pinv + product + Jacobian
-    "eks_backward": (0.0, 204.0),     # S_SMOOTH recursion + schedule; P_SMOOTH is not needed for (J0, J1)
+    "eks_gain": (384.0, 1310.0),      # tape read: packed P-, P+ and S+ (S- is the backward pass's); P+A' + pinv + product + Jacobian
+    "eks_backward": (48.0, 204.0),    # S- read; S_SMOOTH recursion + schedule; P_SMOOTH is not needed for (J0, J1)
     "rollout_cost": (0.0, 91.0),
     "pareto": (0.0, 0.0),
 }
