@@ -197,6 +197,10 @@ EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
   const double gs = SIX ? gamma * s5 : 0.0;
   const double lo = SIX ? (-1.0) / c.sigma : 0.0, hi = SIX ? 1.0 / c.sigma : 0.0;
   const double slope = (SIX && WANT_A25) ? (gamma * c.dt) * (c.sigma / 2.0) : 0.0;
+  // Branch-free per NPI: the constants of the bang-bang rule are loaded (read-only path) whether or
+  // not the input turns out to be missing, so no load waits behind the NaN test of the previous NPI --
+  // fetched inside that branch they were a chain of twelve exposed memory latencies on every day to
+  // optimise (ncu r01) -- and the compiler is free to batch them as far as registers allow.
 #pragma unroll
   for (int j = 0; j < EPI_LMAX; ++j) {
     if (j < L) {
@@ -204,18 +208,17 @@ EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
       const double aj = __ldg(&p->a[j]);
       const double umax = __ldg(&p->u_max[j]);
       if (SIX) {
-        if (uj != uj) {
-          const double phi = eps * __ldg(&p->w[j]) - gs * aj;
-          const double umin = __ldg(&p->u_min[j]);
-          if (WANT_A25) {
-            if (phi > lo && phi < hi) {
-              const double term = (slope * aj) * (umax - umin);
-              r.a25 = FLIP ? (r.a25 + term) : (r.a25 - term);
-            }
-          }
-          const bool to_min = model_legacy(MODEL) ? (phi >= 0.0) : (phi > 0.0);
-          uj = to_min ? umin : umax;
+        const double wj = __ldg(&p->w[j]);
+        const double umin = __ldg(&p->u_min[j]);
+        const bool opt = (uj != uj);
+        const double phi = eps * wj - gs * aj;
+        if (WANT_A25) {
+          const double term = (slope * aj) * (umax - umin);
+          const double a25n = FLIP ? (r.a25 + term) : (r.a25 - term);
+          r.a25 = (opt && phi > lo && phi < hi) ? a25n : r.a25;
         }
+        const bool to_min = model_legacy(MODEL) ? (phi >= 0.0) : (phi > 0.0);
+        uj = opt ? (to_min ? umin : umax) : uj;
       }
       const double g = gamma * aj;
       const double d = umax - uj;
