@@ -385,33 +385,17 @@ def main():
         for _ in range(3):
             step_host()
         fence()
-        # Host-side jitter on the shared box (another tenant, a page-cache flush) shows up as single steps
-        # several times longer than the median.  If that happens the K steps are measured once more and the
-        # better of the two totals is reported; both attempts are kept in the JSON line.
-        attempts = []
-        for attempt in range(2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            walls = []
-            for _ in range(a.steps):
-                tw = time.perf_counter()
-                step_host()
-                walls.append((time.perf_counter() - tw) * 1e3)
-            e1.record()
-            fence()
-            attempts.append((e0.elapsed_time(e1), walls, e0, e1))
-            sys.stderr.write(f"[e2e] attempt {attempt}: per-step wall ms: min {min(walls):.2f} median "
-                             f"{float(np.median(walls)):.2f} max {max(walls):.2f}; kernels {eng.last_kernel_times()}\n")
-            jitter = torch.tensor([1.0 if max(walls) > 3.0 * float(np.median(walls)) else 0.0], device=dev)
-            if world > 1:  # every rank must take the same decision (the steps contain a collective)
-                dist.all_reduce(jitter, op=dist.ReduceOp.MAX)
-            if float(jitter.item()) == 0.0:
-                break
-        tot = torch.tensor([t[0] for t in attempts], dtype=torch.float64, device=dev)
-        if world > 1:  # the attempt is chosen on the max over ranks, as the timing itself
-            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-        best = int(torch.argmin(tot).item())
-        _, walls, e0, e1 = attempts[best]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        walls = []
+        for _ in range(a.steps):
+            tw = time.perf_counter()
+            step_host()
+            walls.append((time.perf_counter() - tw) * 1e3)
+        e1.record()
+        fence()
+        sys.stderr.write(f"[e2e] per-step wall ms: min {min(walls):.2f} median {float(np.median(walls)):.2f} "
+                         f"max {max(walls):.2f}; kernels {eng.last_kernel_times()}\n")
         te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -419,9 +403,8 @@ def main():
         e2e = {"value": units_rank * world / (ms_e2e * 1e-3), "unit": "trajectory-days/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
                "ms_per_step_median": float(np.median(walls)), "ms_per_step_min": float(min(walls)),
-               "attempts_ms_per_step": [t[0] / a.steps for t in attempts],
-               "note": "value uses the total over all K steps of the better attempt; a second attempt is made only "
-                       "when a step of the first took more than 3x the median (host-side jitter on the shared box)"}
+               "ms_per_step_max": float(max(walls)),
+               "note": "value uses the total over all K steps (one attempt)"}
         # parity of the two legs: same bits from the host-memory and device-memory modes
         assert np.array_equal(hout["J0"], out["J0"].cpu().numpy()), "host/device legs disagree"
 

@@ -6,9 +6,11 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <set>
 #include <string>
 #include <utility>
 #include <cstdlib>
+#include <chrono>
 #include <vector>
 
 #include "epi_device.cuh"
@@ -46,6 +48,9 @@ struct epi_ctx {
   // work of a context is enqueued on ONE stream, so recycling a block is stream-ordered.
   std::multimap<size_t, void *> free_blocks;
   size_t cached_bytes = 0;
+  // (B, bytes per trajectory) shapes that ran as a single wave: while their blocks are still cached the
+  // budget query (cudaMemGetInfo: 0.1-7 ms of driver time, measured) is skipped on a repeated call
+  std::set<std::pair<long long, size_t>> fits;
 };
 
 namespace {
@@ -96,6 +101,7 @@ void trim_cache(epi_ctx *c) {
   for (auto &kv : c->free_blocks) cudaFree(kv.second);
   c->free_blocks.clear();
   c->cached_bytes = 0;
+  c->fits.clear();
 }
 void *ctx_alloc(epi_ctx *c, size_t *bytes_io) {
   size_t bytes = (*bytes_io + 511) & ~(size_t)511;
@@ -232,6 +238,15 @@ long long wave_size(long long B, size_t bytes_per_traj, size_t budget) {
   return w;
 }
 
+// wave size of a batch of B trajectories needing `per` bytes of device memory each
+long long plan_wave(epi_ctx *c, long long B, size_t per) {
+  const auto key = std::make_pair(B, per);
+  if (!c->scratch_limit && c->fits.count(key) && c->cached_bytes >= (size_t)B * per) return B;
+  const long long w = wave_size(B, per, scratch_budget(c));
+  if (w >= B && !c->scratch_limit) c->fits.insert(key);
+  return w;
+}
+
 template <class F>
 int guarded(epi_ctx *ctx, F &&f) {
   if (!ctx) return EPI_ERR_ARG;
@@ -257,6 +272,30 @@ void check_mem(int mem) {
 void finish(epi_ctx *c, int mem) {
   if (mem == EPI_MEM_HOST) CK(cudaStreamSynchronize(c->stream));
 }
+
+// EPI_TRACE_HOST=1: host-side timeline of a call on stderr (where a blocking host-memory call spends
+// its wall time: argument checks, copy/launch enqueue, waiting for the stream)
+struct HostTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  std::string line;
+  explicit HostTrace(const char *what) : on(getenv("EPI_TRACE_HOST") != nullptr) {
+    if (on) { t0 = last = std::chrono::steady_clock::now(); line = what; }
+  }
+  void mark(const char *name) {
+    if (!on) return;
+    auto t = std::chrono::steady_clock::now();
+    char b[64];
+    snprintf(b, sizeof b, " %s %.3f", name, std::chrono::duration<double, std::milli>(t - last).count());
+    line += b;
+    last = t;
+  }
+  ~HostTrace() {
+    if (!on) return;
+    fprintf(stderr, "[epi host trace] %s | total %.3f ms\n", line.c_str(),
+            std::chrono::duration<double, std::milli>(last - t0).count());
+  }
+};
 
 }  // namespace
 
@@ -397,7 +436,7 @@ extern "C" int epi_seirp_batch(epi_ctx *c, const epi_seirp_args *a) {
     const double *rates_shared =
         a->rate_mode == EPI_RATES_SHARED_SERIES ? shared.in(a->rates, (size_t)7 * K) : nullptr;
     const long long Bw = a->mem == EPI_MEM_HOST
-                             ? wave_size(B, (rate_rows + 5 + out_rows) * sizeof(double), scratch_budget(c))
+                             ? plan_wave(c, B, (rate_rows + 5 + out_rows) * sizeof(double))
                              : B;
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
@@ -463,7 +502,7 @@ extern "C" int epi_rollout_cost_batch(epi_ctx *c, const epi_rollout_args *a) {
     const size_t usz = a->u_kind == EPI_U_F64 ? 8 : gen ? 0 : 1;
     size_t per = (size_t)K * L * usz + (a->noise ? (size_t)K * 24 : 0) +
                  ((a->s ? 1 : 0) + (a->i ? 1 : 0) + (a->alpha ? 1 : 0)) * (size_t)K * 8 + 16;
-    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, per, scratch_budget(c)) : B;
+    const long long Bw = a->mem == EPI_MEM_HOST ? plan_wave(c, B, per) : B;
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
       Call w(c, a->mem);
@@ -536,7 +575,7 @@ extern "C" int epi_npicost_batch(epi_ctx *c, const epi_npicost_args *a) {
     Call shared(c, a->mem);
     const double *wts = shared.in(a->weights, (size_t)n_groups * a->T * a->L);
     const long long Bw = a->mem == EPI_MEM_HOST
-                             ? wave_size(B, ((size_t)a->T * (a->L + 1) + 2) * 8, scratch_budget(c)) : B;
+                             ? plan_wave(c, B, ((size_t)a->T * (a->L + 1) + 2) * 8) : B;
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
       Call w(c, a->mem);
@@ -566,7 +605,7 @@ extern "C" int epi_si_controlled_batch(epi_ctx *c, const epi_si_args *a) {
     if (!a->alpha || !a->beta || !a->s0 || !a->i0 || !a->s || !a->i) bad_arg("epi_si_controlled_batch: null array");
     reset_phases(c);
     const long long B = a->B;
-    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, ((size_t)3 * a->K + 3) * 8, scratch_budget(c)) : B;
+    const long long Bw = a->mem == EPI_MEM_HOST ? plan_wave(c, B, ((size_t)3 * a->K + 3) * 8) : B;
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
       Call w(c, a->mem);
@@ -673,7 +712,7 @@ extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
     const double *Q = shared.in(a->Q, (size_t)4 * n_groups);
     const double *R = shared.in(a->R, (size_t)n_groups);
     const size_t per = (size_t)T * (1 + 2 + 2 + 4 + 4 + 2 + 2 + 4 + 1 + 1) * 8 + 16;
-    const long long Bw = a->mem == EPI_MEM_HOST ? wave_size(B, per, scratch_budget(c)) : B;
+    const long long Bw = a->mem == EPI_MEM_HOST ? plan_wave(c, B, per) : B;
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
       Call w(c, a->mem);
@@ -790,7 +829,7 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
       per += (a->P_SMOOTH ? (size_t)T * MM * 8 : 0);
       per += ((a->innovations ? 1 : 0) + (a->rho ? 1 : 0)) * (size_t)T * 8 + 16;
     }
-    const long long Bw = wave_size(B, per, scratch_budget(c));
+    const long long Bw = plan_wave(c, B, per);
 
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
@@ -927,10 +966,12 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     if (a->u_knee && !a->I_opt) bad_arg("epi_sweep: u_knee needs I_opt");
     if (a->lean && a->P_first) bad_arg("epi_sweep: P_first needs the full smoother (lean = 0)");
     reset_phases(c);
+    HostTrace tr("epi_sweep");
     const int M = 6, MM = 36, PF = 21, T = a->T, L = a->L, Tf = a->T - a->T_hist;
     const long long nR = a->n_regions, B = nR * a->n_eps;
     const bool host = a->mem == EPI_MEM_HOST;
     if (host) validate_params_host(a->prm, nR, L, EPI_MODEL_OPTCTRL);
+    tr.mark("validate");
 
     Call shared(c, a->mem);
     const epi_model_params *prm = shared.in(a->prm, (size_t)nR);
@@ -960,6 +1001,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     if (a->u_fore && host)
       shared.pend.push_back({a->u_fore, u_fore_dev, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, (size_t)Tf * L * B * 8, 1});
 
+    tr.mark("h2d_enqueue");
     // per-(region, day) input pre-pass: days whose NPIs are all given share their input term and cost
     double *dot_grp = (double *)shared.dalloc((size_t)nR * T * 8);
     double *cost_grp = (double *)shared.dalloc((size_t)nR * T * 8);
@@ -976,7 +1018,8 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     size_t per = (size_t)(Tn > 1 ? Tn - 1 : 1) * MM * 8 + (size_t)2 * Tn * M * 8 + (size_t)2 * Tn * PF * 8 + (size_t)2 * T * 8;
     if (host && a->noise) per += (size_t)Tf * 24;
     if (host && a->P_first) per += (size_t)MM * 8;
-    const long long Bw = wave_size(B, per, scratch_budget(c));
+    const long long Bw = plan_wave(c, B, per);
+    tr.mark("budget");
 
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
@@ -1074,6 +1117,8 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       ph.end();
     }
     shared.flush();
+    tr.mark("launch_enqueue");
     finish(c, a->mem);
+    tr.mark("sync");
   });
 }
