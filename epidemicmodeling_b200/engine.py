@@ -100,13 +100,16 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._lib.epi_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+        self._bound_stream = cuda_stream_ptr or None
 
     def use_torch_stream(self):
         """Run on torch's current stream so torch.cuda.Event timing brackets the kernels.
         torch's default stream is the legacy NULL stream; epi_set_stream treats NULL as
         "the context's own stream", so it is passed as the cudaStreamLegacy handle (0x1)."""
-        ptr = torch.cuda.current_stream(self.device).cuda_stream
-        self.set_stream(ptr if ptr else 0x1)
+        ptr = torch.cuda.current_stream(self.device).cuda_stream or 0x1
+        if ptr != getattr(self, "_bound_stream", None):
+            self.set_stream(ptr)
+            self._bound_stream = ptr
 
     def set_scratch_limit(self, nbytes):
         self._ck(self._lib.epi_set_scratch_limit(self._h, int(nbytes)))
@@ -137,6 +140,10 @@ class Engine:
             for a in dev:
                 if not a.is_cuda:
                     raise ValueError("torch inputs must be CUDA tensors (EPI_MEM_DEVICE)")
+            # Device-memory calls are asynchronous: they are enqueued on torch's CURRENT stream, so they are
+            # ordered after whatever produced the input tensors and torch's allocator recycles a tensor only
+            # in stream order (a private stream would race with both).
+            self.use_torch_stream()
             return K.MEM_DEVICE
         return K.MEM_HOST
 
