@@ -72,7 +72,6 @@ class Engine:
         self._h = h
         self.device = int(device)
         self._keep = []
-        self._inflight = []
 
     # -- context ------------------------------------------------------------
     def close(self):
@@ -96,7 +95,6 @@ class Engine:
 
     def sync(self):
         self._ck(self._lib.epi_sync(self._h))
-        self._inflight = []
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self._lib.epi_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
@@ -192,11 +190,9 @@ class Engine:
         return C.addressof(prm)
 
     def _done(self):
-        # device-mode calls return before their kernels ran: keep the arrays of the
-        # most recent calls alive until sync() so the allocator cannot recycle them
-        self._inflight.append(self._keep)
-        if len(self._inflight) > 8:
-            self._inflight.pop(0)
+        # The arrays of a call need no keeping alive past its return: host-memory calls are blocking, and
+        # device-memory calls run on torch's current stream (_mode), where torch's caching allocator
+        # recycles a freed tensor in stream order, i.e. after the kernels that still read it.
         self._keep = []
 
     # -- SEIRP ----------------------------------------------------------------
