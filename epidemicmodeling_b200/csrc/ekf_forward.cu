@@ -72,7 +72,11 @@ void launch_group_day(const epi_model_params *prm, const double *u, const double
 // Days [k_begin, k_end) of trajectory b.  k_begin == 0 starts from the initial conditions, a later
 // start resumes from the a-priori page (S_MINUS, P_MINUS) of day k_begin that the previous segment
 // left on the tape -- without the innovation monitor that page IS the whole filter state.
-template <int MODEL, bool MONITOR, bool TILED>
+// PLAIN = the common call shape fixed at compile time: constant Q (EPI_Q_CONST) and none of the optional
+// per-day outputs (u_opt, K_GAIN, innov).  The run-time dispatch on these inside the day loop cost 8 % of the
+// loop's instructions and 10 % of the pass (4.08 -> 3.65 ms on the sweep): the loop body is larger than the
+// instruction cache can hold for two warps per scheduler.
+template <int MODEL, bool MONITOR, bool TILED, bool PLAIN = false>
 EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, const int k_end, double *win) {
   constexpr int M = model_dim(MODEL);
   constexpr bool LEG = model_legacy(MODEL);
@@ -86,6 +90,7 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
   const TrajIn in = traj_inputs(P, b, M);
   const ModelConsts mc = load_consts(in.prm);
   const int T = P.T, L = P.L, W = P.W;
+  const int q_mode = PLAIN ? (int)EPI_Q_CONST : P.q_mode;
   const double gamma = P.gamma, beta = P.beta, v_bar = P.v_bar, eps = in.eps;
   const InvDiv by_gamma = make_invdiv(gamma);
 
@@ -179,7 +184,7 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
         for (int i = 0; i < M; ++i) K[i] = div_fast(PCt[i], by_denom, rng);
         if (!(by_denom.ok && rng.safe())) {
 #pragma unroll
-          for (int i = 0; i < M; ++i) K[i] = PCt[i] / denom;
+          for (int i = 0; i < M; ++i) K[i] = slow_div(PCt[i], denom);  // (out of line: cold, and the loop body must stay small)
         }
       }
       double Mx[M][3];  // I - K*C, columns 0..2 (columns 3.. are identity)
@@ -206,7 +211,7 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
           for (int i = 0; i < M; ++i)
 #pragma unroll
             for (int j = 0; j < M; ++j)
-              Pp.at(i, j) = EXACT ? MP(i, j) / gamma : div_fast(MP(i, j), by_gamma, rng);  // legacy :64
+              Pp.at(i, j) = EXACT ? slow_div(MP(i, j), gamma) : div_fast(MP(i, j), by_gamma, rng);  // legacy :64
         } else {
           // :127 Joseph form, :138 symmetrisation
 #pragma unroll
@@ -219,8 +224,8 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
               if (i >= 3) mji = mji + MP(j, i);
               const double nij = mij + (K[i] * Rk) * K[j];
               const double nji = mji + (K[j] * Rk) * K[i];
-              const double pij = EXACT ? nij / gamma : div_fast(nij, by_gamma, rng);
-              const double pji = EXACT ? nji / gamma : div_fast(nji, by_gamma, rng);
+              const double pij = EXACT ? slow_div(nij, gamma) : div_fast(nij, by_gamma, rng);
+              const double pji = EXACT ? slow_div(nji, gamma) : div_fast(nji, by_gamma, rng);
               Pp.at(i, j) = (pij + pji) / 2.0;
             }
         }
@@ -246,7 +251,7 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
 
     // :155-157 state update + Jacobian at s(k|k) (one pass over the NPI inputs, or the
     // per-group value when the day has no input to optimise)
-    double *uo = P.u_opt.p ? P.u_opt.p + (size_t)P.u_opt.off + b + (size_t)pos * L * P.u_opt.stride : nullptr;
+    double *uo = (!PLAIN && P.u_opt.p) ? P.u_opt.p + (size_t)P.u_opt.off + b + (size_t)pos * L * P.u_opt.stride : nullptr;
     const double *ud = in.u + (size_t)pos * in.u_ts;
     double dotv, a25 = 0.0;
     const double pre = pre_cur;
@@ -275,14 +280,14 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
       for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = 0; j < M; ++j)
-          Pm.at(i, j) = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
+          Pm.at(i, j) = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, q_mode, M, k, i, j);
     } else {
 #pragma unroll
       for (int i = 0; i < M; ++i)
 #pragma unroll
         for (int j = i; j < M; ++j) {
-          const double pij = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, P.q_mode, M, k, i, j);
-          const double pji = mul_X_At_ij<M>(AP, A, j, i) + q_elem(in.Q, P.q_mode, M, k, j, i);
+          const double pij = mul_X_At_ij<M>(AP, A, i, j) + q_elem(in.Q, q_mode, M, k, i, j);
+          const double pji = mul_X_At_ij<M>(AP, A, j, i) + q_elem(in.Q, q_mode, M, k, j, i);
           Pm.at(i, j) = (pij + pji) / 2.0;
         }
     }
@@ -297,12 +302,12 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
       for (int i = 0; i < M; ++i) d[tSp.f(i)] = sp[i];
       tape_store_cov<M, SYM, TILED>(Pp, tPp, tPp.at_day(pos));
     }
-    if (P.K_GAIN.p) {
+    if (!PLAIN && P.K_GAIN.p) {
       double *d = P.K_GAIN.p + (size_t)P.K_GAIN.off + b + (size_t)pos * M * P.K_GAIN.stride;
 #pragma unroll
       for (int i = 0; i < M; ++i) d[(size_t)i * P.K_GAIN.stride] = K[i];
     }
-    if (P.innov.p) P.innov.p[(size_t)pos * P.innov.stride + P.innov.off + b] = innov;
+    if (!PLAIN && P.innov.p) P.innov.p[(size_t)pos * P.innov.stride + P.innov.off + b] = innov;
 
     if (MONITOR) {
       // :172-185 innovation whiteness monitor.  The three W-long windows live in
@@ -349,11 +354,15 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
 #ifndef EPI_FWD_MIN_BLOCKS6
 #define EPI_FWD_MIN_BLOCKS6 8  // m = 6: 32-thread CTAs, 8 per SM = 255 registers (measured best)
 #endif
-template <int MODEL, bool MONITOR, bool TILED>
+template <int MODEL, bool MONITOR, bool TILED, bool PLAIN = false>
 __global__ void __launch_bounds__((model_dim(MODEL) == 6) ? 32 : 64, (model_dim(MODEL) == 6) ? EPI_FWD_MIN_BLOCKS6 : 4)
 ekf_forward_kernel(const __grid_constant__ EkfParams P) {
   extern __shared__ double win[];  // MONITOR: [3][W][blockDim.x]
-  forward_days<MODEL, MONITOR, TILED>(P, blockIdx.x * blockDim.x + threadIdx.x, 0, P.T, win);
+  forward_days<MODEL, MONITOR, TILED, PLAIN>(P, blockIdx.x * blockDim.x + threadIdx.x, 0, P.T, win);
+}
+// the PLAIN call shape (see forward_days)
+static bool forward_plain(const EkfParams &p) {
+  return p.q_mode == EPI_Q_CONST && !p.u_opt.p && !p.K_GAIN.p && !p.innov.p;
 }
 
 // Persistent, time-segmented form for batches of only a few waves (the 236 x 250 sweep is
@@ -364,7 +373,7 @@ ekf_forward_kernel(const __grid_constant__ EkfParams P) {
 // predecessor (same tile, previous segment) through a per-tile progress word; predecessors
 // always have a lower item number, so they are running or done and the wait cannot deadlock.
 // sync[0] = item counter, sync[1 + tile] = segments of that tile finished (zeroed by the host).
-template <int MODEL, bool TILED>
+template <int MODEL, bool TILED, bool PLAIN = false>
 __global__ void __launch_bounds__(32, EPI_FWD_MIN_BLOCKS6) ekf_forward_segmented_kernel(const __grid_constant__ EkfParams P) {
   const int S = P.fwd_segments, T = P.T, k0 = P.k0;
   const int n_tiles = (P.B + 31) / 32;
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(32, EPI_FWD_MIN_BLOCKS6) ekf_forward_segmented
       __syncwarp();
       __threadfence();
     }
-    if (ke > kb || seg == 0) forward_days<MODEL, false, TILED>(P, tile * 32 + lane, kb, ke, nullptr);
+    if (ke > kb || seg == 0) forward_days<MODEL, false, TILED, PLAIN>(P, tile * 32 + lane, kb, ke, nullptr);
     __threadfence();
     __syncwarp();
     if (lane == 0) atomicExch(P.fwd_sync + 1 + tile, seg + 1);
@@ -401,6 +410,8 @@ static void launch_fwd_model(const EkfParams &p, cudaStream_t st, bool monitor) 
     cudaFuncSetAttribute(ekf_forward_kernel<MODEL, true, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)smem);
     ekf_forward_kernel<MODEL, true, TILED><<<grid, block, smem, st>>>(p);
+  } else if (TILED && forward_plain(p)) {
+    ekf_forward_kernel<MODEL, false, TILED, TILED><<<grid, block, 0, st>>>(p);  // (PLAIN exists for TILED only)
   } else {
     ekf_forward_kernel<MODEL, false, TILED><<<grid, block, 0, st>>>(p);
   }
@@ -430,7 +441,8 @@ static bool launch_fwd_segmented(const EkfParams &p, cudaStream_t st) {
     const int tiles = (p.B + 31) / 32;
     int grid = tiles < slots ? tiles : slots;
     if (const char *e = getenv("EPI_FWD_GRID")) grid = atoi(e);  // tuning experiments
-    ekf_forward_segmented_kernel<MODEL, true><<<grid, 32, 0, st>>>(p);
+    if (forward_plain(p)) ekf_forward_segmented_kernel<MODEL, true, true><<<grid, 32, 0, st>>>(p);
+    else ekf_forward_segmented_kernel<MODEL, true><<<grid, 32, 0, st>>>(p);
     return true;
   } else {
     return false;
