@@ -10,8 +10,11 @@
 
 namespace epi {
 
+#ifndef EPI_GAIN_BLOCK
+#define EPI_GAIN_BLOCK 128
+#endif
 #ifndef EPI_GAIN_MIN_BLOCKS
-#define EPI_GAIN_MIN_BLOCKS 4
+#define EPI_GAIN_MIN_BLOCKS (512 / EPI_GAIN_BLOCK)
 #endif
 
 // A_k = df/ds at S_PLUS(:,k)  (GenericExtendedKalmanFilter.m:206)
@@ -38,7 +41,7 @@ EPI_DI void gain_jacobian(const TrajIn &in, const Tape<TILED> &tSp, int pos, int
 }
 
 template <int MODEL, bool TILED>
-__global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(const __grid_constant__ EkfParams P) {
+__global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(const __grid_constant__ EkfParams P) {
   constexpr int M = model_dim(MODEL);
   constexpr bool LEG = model_legacy(MODEL);
   constexpr bool SYM = !LEG;
@@ -63,7 +66,7 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
   const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1 - k0, b, k0);
 
   // rotation stack of pinv_sym (generic models only)
-  __shared__ double rot_stack[LEG ? 1 : RotStack<M, 128>::SMEM_WORDS];
+  __shared__ double rot_stack[LEG ? 1 : RotStack<M, EPI_GAIN_BLOCK>::SMEM_WORDS];
   Mat<M, false> A, Jm;
   int rank = M;
   bool bad = false, stored = false;
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(128, EPI_GAIN_MIN_BLOCKS) eks_gain_kernel(cons
 #ifdef EPI_GAIN_SKIP_PINV  // experiment: cost of everything but the eigen-iteration
       X = Pn;
 #else
-      rank = pinv_sym<M, 128>(Pn, X, rot_stack + threadIdx.x);
+      rank = pinv_sym<M, EPI_GAIN_BLOCK>(Pn, X, rot_stack + threadIdx.x);
 #endif
       // the state Jacobian is evaluated AFTER the eigen-iteration so that neither its entries nor
       // the model constants are live (or spilled) across it
@@ -178,7 +181,7 @@ static void launch_gain_model(const EkfParams &p, cudaStream_t st) {
   if (p.T - p.k0 < 2) return;
   const size_t Bpad = (size_t)((p.B + 31) / 32) * 32;
   const size_t total = (size_t)(p.T - 1 - p.k0) * Bpad;
-  const int block = 128;
+  const int block = EPI_GAIN_BLOCK;
   const unsigned grid = (unsigned)((total + block - 1) / block);
   if (p.tiled) eks_gain_kernel<MODEL, true><<<grid, block, 0, st>>>(p);
   else eks_gain_kernel<MODEL, false><<<grid, block, 0, st>>>(p);
