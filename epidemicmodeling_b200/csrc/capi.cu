@@ -51,6 +51,10 @@ struct epi_ctx {
   // (B, bytes per trajectory) shapes that ran as a single wave: while their blocks are still cached the
   // budget query (cudaMemGetInfo: 0.1-7 ms of driver time, measured) is skipped on a repeated call
   std::set<std::pair<long long, size_t>> fits;
+  // side stream for host-memory inputs that the first kernels of a call do not read (the sweep's cost
+  // weights: 12.7 MB that upload beside the forward pass instead of in front of it)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -339,6 +343,12 @@ extern "C" void epi_destroy(epi_ctx *c) {
   reset_phases(c);
   trim_cache(c);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->copy_ev[0]);
+    cudaEventDestroy(c->copy_ev[1]);
+  }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
@@ -986,7 +996,31 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     const double *Q = shared.in(a->Q, (size_t)nR * MM);
     const double *x0 = shared.in(a->x0, (size_t)nR * 3);
     const double *nch = shared.in(a->newcases_hist, (size_t)nR * a->T_hist);
-    const double *wts = shared.in(a->weights, (size_t)nR * T * L);
+    // The cost weights are first read by the backward pass: in host mode they are uploaded on the side
+    // stream, beside the forward pass, and the launching stream picks them up through an event.
+    const double *wts = nullptr;
+    bool wts_deferred = false;
+    struct CopyGuard {  // never leave a copy in flight into a block that is about to be recycled
+      cudaStream_t s = nullptr;
+      ~CopyGuard() { if (s) cudaStreamSynchronize(s); }
+    } copy_guard;
+    if (host && !getenv("EPI_NO_SIDE_COPY")) {
+      if (!c->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
+      }
+      double *d = (double *)shared.dalloc((size_t)nR * T * L * sizeof(double));
+      CK(cudaEventRecord(c->copy_ev[0], c->stream));  // the block may still be read by work queued earlier
+      CK(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
+      CK(cudaMemcpyAsync(d, a->weights, (size_t)nR * T * L * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+      CK(cudaEventRecord(c->copy_ev[1], c->copy_stream));
+      copy_guard.s = c->copy_stream;
+      wts = d;
+      wts_deferred = true;
+    } else {
+      wts = shared.in(a->weights, (size_t)nR * T * L);
+    }
     const double *nstd = shared.in(a->noise_std, (size_t)nR * 3);
     // whole-batch outputs (the Pareto step needs every epsilon of a region)
     double *J0 = shared.out(a->J0, (size_t)B);
@@ -1007,7 +1041,9 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     double *cost_grp = (double *)shared.dalloc((size_t)nR * T * 8);
     {
       PhaseScope ph(c, "group_day");
-      launch_group_day(prm, u, wts, (int)nR, T, L, dot_grp, cost_grp, c->stream);
+      // (deferred weights: the input terms now, the per-day costs once the weights have arrived)
+      launch_group_day(prm, u, wts_deferred ? nullptr : wts, (int)nR, T, L, dot_grp, wts_deferred ? nullptr : cost_grp,
+                       c->stream);
       check_launch(c, 1);
       ph.end();
     }
@@ -1071,6 +1107,12 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         launch_eks_gain(p, c->stream);
         check_launch(c, 1);
         ph.end();
+      }
+      if (wts_deferred) {  // first consumer of the weights and of cost_grp
+        CK(cudaStreamWaitEvent(c->stream, c->copy_ev[1], 0));
+        launch_group_day(prm, u, wts, (int)nR, T, L, dot_grp, cost_grp, c->stream);  // same dot_grp bits again + costs
+        check_launch(c, 1);
+        wts_deferred = false;
       }
       {
         PhaseScope ph(c, "eks_backward");
