@@ -381,6 +381,37 @@ def test_ekf6_per_trajectory_epsilon_batch(engine):
     assert out["status"].shape == (eps.size,)
 
 
+@pytest.mark.parametrize("model", ["sialpha", "optctrl"])
+def test_forward_instantiations_agree(engine, model):
+    """The forward pass has three instantiations per model: strided tape (every output requested), tiled
+    scratch tape with optional per-day outputs (run-time dispatch in the day loop) and tiled PLAIN (constant
+    Q, no optional outputs fixed at compile time: csrc/ekf_forward.cu).  Same bits from all three, for a
+    ragged batch that spans several tiles."""
+    if model == "sialpha":
+        inp, b, x, nRep = _ekf3_replicate_batch(nR=3, nRep=27)
+        B, T, L = x.shape[1], b["T"], b["L"]
+        args = (K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"], b["s_final"],
+                b["Ps_final"])
+        kw = dict(B=B, T=T, L=L, G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=b["beta"],
+                  gamma=b["gamma"], W=b["W"])
+    else:
+        c = cases.ekf6_case(1, T_hist=40, T_fore=20)
+        eps = np.concatenate([np.logspace(-9, -0.001, 40), [0.3, 0.999, 1e-12]])
+        T, L = c["u"].shape[1], 12
+        cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+        args = (K.MODEL_OPTCTRL, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], c["R_v"], cm(c["Q_w"]),
+                c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]))
+        kw = dict(B=eps.size, T=T, L=L, G=eps.size, epsilon=eps, r_mode=K.R_PERDAY, fixed_R=False, beta=1.0,
+                  gamma=0.995, W=21)
+    full = engine.ekf_eks(*args, **kw)                                                   # strided tape
+    opt = engine.ekf_eks(*args, outputs=("S_SMOOTH", "u_opt", "K_GAIN", "innovations", "u_opt_smooth"), **kw)
+    plain = engine.ekf_eks(*args, outputs=("S_SMOOTH", "u_opt_smooth"), **kw)            # tiled, PLAIN
+    for k in ("S_SMOOTH", "u_opt", "K_GAIN", "innovations", "u_opt_smooth"):
+        assert_bits(opt[k], full[k], f"tiled+optional outputs: {k}")
+    for k in ("S_SMOOTH", "u_opt_smooth"):
+        assert_bits(plain[k], full[k], f"tiled PLAIN: {k}")
+
+
 @pytest.mark.parametrize("nS", [10, 257])
 def test_generated_schedules_match_oracle_and_supplied(engine, nS):
     """EPI_U_PHILOX: the schedules drawn in the kernel are the oracle's (bit for bit), integrating
