@@ -8,6 +8,8 @@ $B > gpurun_out/plain.log 2>&1 && timeout 600 ncu --metrics gpu__time_duration.s
 for k in ekf_forward eks_gain eks_backward; do timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/prof_$k -f $B > gpurun_out/ncu_$k.log 2>&1; done
 C="python tools/bench_configs.py --only 2 --scale 0.5"
 $C > gpurun_out/c2_plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:seirp_staged -s 1 -c 1 -o gpurun_out/prof_seirp_staged -f $C > gpurun_out/ncu_seirp.log 2>&1
+C5="python tools/bench_configs.py --only 5 --scale 0.25"
+$C5 > gpurun_out/c5_plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_staged -s 1 -c 1 -o gpurun_out/prof_rollout_staged -f $C5 > gpurun_out/ncu_rollout.log 2>&1
 timeout 800 python tools/bench_configs.py > gpurun_out/configs.log 2>&1
 tail -2 gpurun_out/smoke.log; tail -3 gpurun_out/pytest.log; tail -2 gpurun_out/bench.err; cut -c1-300 gpurun_out/bench_reference.log | tail -1
 python - <<PY
