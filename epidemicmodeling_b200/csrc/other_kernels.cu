@@ -490,8 +490,14 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
 
 template <int U_KIND>
 static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
-  constexpr int SB = 256;
-  constexpr int TT = (U_KIND == EPI_U_U8) ? 16 : 2;
+#ifndef EPI_ROLL_SB  // trajectories per CTA = bytes per uint8 row piece of a TMA bulk copy
+#define EPI_ROLL_SB 256
+#endif
+#ifndef EPI_ROLL_TT  // days per stage (uint8 schedules)
+#define EPI_ROLL_TT 16
+#endif
+  constexpr int SB = (U_KIND == EPI_U_U8) ? EPI_ROLL_SB : 256;
+  constexpr int TT = (U_KIND == EPI_U_U8) ? EPI_ROLL_TT : 2;
   const size_t esz = (U_KIND == EPI_U_U8) ? 1 : 8;
   // TMA bulk copies need 16-byte aligned, 16-byte multiple rows
   if (p.K < 1 || p.B < 8 * SB || (((size_t)p.B * esz) & 15) || (((size_t)p.u_stride * esz) & 15) ||
