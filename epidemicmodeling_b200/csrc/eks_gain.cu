@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
   const Tape<true> tJ = make_tape<true>(P.J, MM, T - 1 - k0, b, k0);
 
   // rotation stack of pinv_sym (generic models only)
-  __shared__ double rot_stack[LEG ? 1 : RotStack<M, EPI_GAIN_BLOCK>::SMEM_WORDS];
+  extern __shared__ double rot_stack[];  // generic models: [DS][EPI_GAIN_BLOCK] words (dynamic: 48 KB and more)
   Mat<M, false> A, Jm;
   int rank = M;
   bool bad = false, stored = false;
@@ -183,8 +183,15 @@ static void launch_gain_model(const EkfParams &p, cudaStream_t st) {
   const size_t total = (size_t)(p.T - 1 - p.k0) * Bpad;
   const int block = EPI_GAIN_BLOCK;
   const unsigned grid = (unsigned)((total + block - 1) / block);
-  if (p.tiled) eks_gain_kernel<MODEL, true><<<grid, block, 0, st>>>(p);
-  else eks_gain_kernel<MODEL, false><<<grid, block, 0, st>>>(p);
+  constexpr int M = model_dim(MODEL);
+  const size_t smem = model_legacy(MODEL) ? 0 : sizeof(double) * RotStack<M, EPI_GAIN_BLOCK>::SMEM_WORDS;
+  if (p.tiled) {
+    cudaFuncSetAttribute(eks_gain_kernel<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eks_gain_kernel<MODEL, true><<<grid, block, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(eks_gain_kernel<MODEL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    eks_gain_kernel<MODEL, false><<<grid, block, smem, st>>>(p);
+  }
 }
 
 void launch_eks_gain(const EkfParams &p, cudaStream_t st) {
