@@ -418,12 +418,16 @@ static void launch_fwd_model(const EkfParams &p, cudaStream_t st, bool monitor) 
 }
 
 // Number of time segments for `tiles` one-warp CTAs on `slots` resident CTAs (1 = plain launch).
-// Measured on the 1844-tile sweep (B200, 1184 slots): the kernel saturates the SM from ~6 warps
-// per SM on, so segmenting only trims the idle tail of the last wave: S = 1 / 3 / 7 / 12 / 24 ->
-// 4.75 / 4.45 / 4.77 / 4.97 / 5.29 ms (each resume costs ~0.02 ms).  Three segments whenever the
-// batch is a few, non-integral waves.
+// The kernel saturates the SM from ~6 of its 8 warps on, so segmenting only trims the idle tail of the
+// last wave, and every extra segment adds waits on predecessors.  Measured with the PLAIN kernel (B200,
+// 1184 slots; forward ms for S = 1 / 2 / 3):  1422 tiles (1.20 waves) 2.85 / 3.03 / 3.29 - 1844 tiles
+// (1.56, the 236 x 250 sweep) 3.52 / 3.04 / 3.83 - 2344 tiles (1.98) 3.66 / 3.51 / 3.53 - 2961 tiles (2.50)
+// 5.00 / 4.63 / 4.47 - 4141 tiles (3.50) 6.20 / 6.36 / 6.09.
 int forward_segments(long long tiles, int slots) {
   if (tiles <= slots || tiles > 6LL * slots || tiles % slots == 0) return 1;
+  const double waves = (double)tiles / (double)slots;
+  if (waves <= 1.3) return 1;
+  if (waves <= 2.25) return 2;
   return 3;
 }
 
