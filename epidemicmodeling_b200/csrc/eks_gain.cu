@@ -114,7 +114,11 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
       };
       double prow[M];
       load_row(0, prow);
-#pragma unroll 1  // rolled: the row body is ~100 instructions, 6 copies of it would not fit the i-cache budget
+#ifndef EPI_GAIN_ROW_UNROLL
+#define EPI_GAIN_ROW_UNROLL 2  // row body ~100 instructions; measured kernel ms for 1 / 2 / 3 / 6: 6.49 / 6.39 / 6.59 / 6.38
+#endif
+      constexpr int kRowUnroll = EPI_GAIN_ROW_UNROLL;
+#pragma unroll kRowUnroll
       for (int i = 0; i < M; ++i) {
         double pnext[M], pat[M];
         load_row(i + 1 < M ? i + 1 : i, pnext);  // next row's loads in flight during this row's products
