@@ -13,8 +13,12 @@ the path's single collective: an all-gather of the per-shard (J0, J1).
   e2e   : the same through the blocking host-memory C-ABI call (pinned host buffers,
           H2D + D2H inside the timed region) -- the call a MATLAB/Octave host makes
   roofline / cpu_baseline : see DESIGN.md "Measurement"
-Multi-GPU: one process per GPU (torchrun), weak scaling: every rank runs a full
-236-region replica (different synthetic seeds), no data-path collective except the gather.
+Multi-GPU (torchrun, one process per GPU): STRONG scaling -- the ONE 236-region sweep is sharded
+by region (contiguous blocks of ceil(236/N) regions, workloads.shard_regions), each rank keeps its
+shard's inputs resident, and a step ends with the path's single collective, an all-gather of the
+per-shard (J0, J1) over NCCL, followed by the Pareto step on the gathered costs.  `value` =
+236 x 250 x 561 trajectory-days / step time (max over ranks).  The replicated (weak) form of round 1
+is reported under "replica_weak" for reference.
 """
 import argparse
 import json
@@ -55,6 +59,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-lean", action="store_true", help="skip the extra lean-mode leg (profiling runs)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the configs 2/3/5 block")
+    ap.add_argument("--no-replica", action="store_true", help="N > 1: skip the replicated (weak-scaling) extra leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
@@ -168,13 +174,23 @@ class NvmlSampler:
         return out
 
 
-def build_inputs(a, rank):
+def build_inputs(a, rank=0):
+    """The ONE synthetic workload (same seeds on every rank); `rank` only offsets the seeds of the
+    replicated extra leg."""
     from epidemicmodeling_b200 import synthetic as syn
-    # weak scaling: every rank gets its own 236-region replica (different seeds)
     inp = syn.sweep_inputs(n_regions=a.regions, T_hist=a.t_hist, T_fore=a.t_fore, seed_u=2 + 100003 * rank,
                            seed_x=3 + 100003 * rank)
     eps = syn.epsilon_grid_xprize02(a.eps)
     return inp, eps
+
+
+def host_threads():
+    """Threads the CPU arm may use: the process's affinity mask, NOT OpenMP's default --
+    torchrun exports OMP_NUM_THREADS=1 to its children, which round 1's reference arm obeyed."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -205,16 +221,16 @@ def oracle_fixed_input(inp):
 
 
 def cpu_sample(a, inp, eps, seconds):
-    """Time the CPU oracle (all host threads, OpenMP over trajectories) on a bounded sample
-    of the same workload: the first n regions x all epsilon.  Returns (value, cores, sample, n)."""
+    """Size a bounded sample of the workload (the first n regions x all epsilon) for the CPU oracle
+    on all host threads (OpenMP over trajectories).  Returns (n, cores, seconds for one region)."""
     from oracle import oracle as orc
-    T = a.t_hist + a.t_fore
-    cores = orc.num_threads()
+    cores = host_threads()
     probe = inp[:1]
     regs = oracle_regions(probe, oracle_fixed_input(probe))
     t0 = time.perf_counter()
     orc.sweep_batch(regs, eps, n_threads=cores)
     t1 = time.perf_counter() - t0
+    # one region alone cannot use more threads than it has trajectories; scale the estimate accordingly
     n = int(max(1, min(len(inp), round(seconds / max(t1, 1e-6)))))
     return n, cores, t1
 
@@ -222,12 +238,13 @@ def cpu_sample(a, inp, eps, seconds):
 def run_reference(a):
     """--impl reference: the reference's CPU implementation of the path.  Octave/MATLAB do not
     exist in this image, so this is the C oracle (a line-by-line port of the .m files) with all
-    host threads -- kind "port".  Each step = a bounded sample (n regions x all epsilon)."""
+    host threads -- kind "port".  Each step = a bounded sample (n regions x all epsilon).
+    Under torchrun rank 0 alone runs it, with every host thread the process may use."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import oracle as orc
-    inp, eps = build_inputs(a, 0)
+    inp, eps = build_inputs(a)
     T = a.t_hist + a.t_fore
     budget = max(2.0, min(a.cpu_seconds, 120.0 / max(1, a.steps + a.warmup)))
     n, cores, _ = cpu_sample(a, inp, eps, budget)
@@ -244,11 +261,12 @@ def run_reference(a):
     sample_s = f"{n} of {a.regions} regions x {a.eps} eps x {T} days per step (OpenMP over trajectories)"
     line = {"impl": "reference", "metric": "trajectory_days_per_sec", "value": val, "unit": "trajectory-days/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if a.gpus > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a), "note": "CPU oracle port of the reference .m files; "
-                       "Octave/MATLAB absent from the image"},
+                       "Octave/MATLAB absent from the image; a CPU job: the same host threads whatever --gpus says"},
             "cpu_baseline": {"value": val, "unit": "trajectory-days/s", "cores": cores, "kind": "port",
-                             "sample": sample_s},
+                             "sample": sample_s, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": val, "unit": "trajectory-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -256,6 +274,21 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- our arm
+def timed_steps(step, n, fence, drain=None):
+    """CUDA-event time of n calls of step() on torch's current stream, fenced on both sides."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    e0.record()
+    for _ in range(n):
+        step()
+    if drain:
+        drain()
+    e1.record()
+    fence()
+    return e0.elapsed_time(e1)
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -276,8 +309,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     T = a.t_hist + a.t_fore
-    inp, eps = build_inputs(a, rank)
+    nR, nE = a.regions, a.eps
+    inp_all, eps = build_inputs(a)
+    # strong scaling: this rank's contiguous block of regions (TrainPredictPrescribeNPI.m:93 is the loop)
+    lo, hi = wl.shard_regions(nR, world, rank)
+    per = (nR + world - 1) // world
+    inp = inp_all[lo:hi]
+    n_loc = hi - lo
     eng = Engine(local)
     eng.use_torch_stream()
 
@@ -285,171 +335,212 @@ def main():
     S_fixed = wl.run_fixed_input(eng, inp)
     batch = wl.sweep_batch(inp, S_fixed)
     dbatch = wl.sweep_to_device(batch, eps, dev)
-    nR, nE = a.regions, a.eps
-    out = {"J0": torch.empty((nR, nE), dtype=torch.float64, device=dev),
-           "J1": torch.empty((nR, nE), dtype=torch.float64, device=dev),
-           "on_front": torch.empty((nR, nE), dtype=torch.uint8, device=dev),
-           "I_opt": torch.empty((nR,), dtype=torch.int32, device=dev)}
-    # The one collective of the path (all-gather of the per-shard costs over NVLink) runs on a side stream:
-    # the gather of step i overlaps the sweep of step i+1 (outputs and send/receive buffers double-buffered;
-    # every gather is drained before the timed region closes).
-    outs = [out]
-    comm = None
-    if world > 1:
-        comm = torch.cuda.Stream(device=dev)
-        outs.append({k: torch.empty_like(v) for k, v in out.items()})
-        gathered = [torch.empty((world, 2, nR, nE), dtype=torch.float64, device=dev) for _ in range(2)]
-        send = [torch.empty((2, nR, nE), dtype=torch.float64, device=dev) for _ in range(2)]
-    comm_ev = [None, None]
+    f64, u8, i32 = torch.float64, torch.uint8, torch.int32
+
+    # Output buffers.  N = 1: epi_sweep writes J0/J1/front/knee itself.  N > 1: the shard's costs go into the first
+    # n_loc rows of a [per, nE] send buffer (double-buffered); the all-gather lands them in [N*per, nE], whose first
+    # nR rows are the full (J0, J1) because shards are contiguous blocks; the Pareto step runs on those.
+    nbuf = 2 if world > 1 else 1
+    loc = [{"J0": torch.zeros((per, nE), dtype=f64, device=dev), "J1": torch.zeros((per, nE), dtype=f64, device=dev)}
+           for _ in range(nbuf)]
+    full = [{"J0": torch.empty((world * per, nE), dtype=f64, device=dev),
+             "J1": torch.empty((world * per, nE), dtype=f64, device=dev),
+             "on_front": torch.empty((nR, nE), dtype=u8, device=dev),
+             "I_opt": torch.empty((nR,), dtype=i32, device=dev)} for _ in range(nbuf)]
+    out1 = {"J0": full[0]["J0"][:nR], "J1": full[0]["J1"][:nR], "on_front": full[0]["on_front"], "I_opt": full[0]["I_opt"]}
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    eng_tail = Engine(local) if world > 1 else None      # its own context: the gather/Pareto tail runs on the side stream
+    comm_ev = [None] * nbuf
     step_no = [0]
 
-    def gather_async(i, j0, j1):
-        """enqueue copy + all-gather of buffer set i on the side stream, after the work queued so far"""
+    def sweep_local(i, b=dbatch, e=None):
+        if world == 1:
+            return wl.run_sweep(eng, b, e, out=out1)
+        return wl.run_sweep(eng, b, e, out={"J0": loc[i]["J0"][:n_loc], "J1": loc[i]["J1"][:n_loc]}, want_front=False)
+
+    def tail(i):
+        """the path's single collective + the Pareto step on the gathered costs (current stream)"""
+        dist.all_gather_into_tensor(full[i]["J0"].view(-1), loc[i]["J0"].view(-1))
+        dist.all_gather_into_tensor(full[i]["J1"].view(-1), loc[i]["J1"].view(-1))
+        eng_tail.pareto(full[i]["J0"][:nR], full[i]["J1"][:nR], out=(full[i]["on_front"], full[i]["I_opt"]))
+
+    def tail_async(i):
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(comm):
             comm.wait_event(ready)
-            send[i][0].copy_(j0, non_blocking=True)
-            send[i][1].copy_(j1, non_blocking=True)
-            dist.all_gather_into_tensor(gathered[i].view(-1), send[i].view(-1))
+            tail(i)
             done = torch.cuda.Event()
             done.record(comm)
         comm_ev[i] = done
 
     def drain():
-        """the launching stream waits for every gather in flight (called before a timed region closes)"""
         for e in comm_ev:
             if e is not None:
                 torch.cuda.current_stream().wait_event(e)
 
     def step():
-        i = step_no[0] & 1 if world > 1 else 0
+        """one pass of the hot path; N > 1: the tail of step i overlaps the sweep of step i+1"""
+        i = step_no[0] % nbuf
         step_no[0] += 1
-        if comm_ev[i] is not None:  # buffer set i is free once its previous gather has finished
+        if comm_ev[i] is not None:      # buffer set i is free once its previous tail has finished
             torch.cuda.current_stream().wait_event(comm_ev[i])
-        wl.run_sweep(eng, dbatch, None, out=outs[i])
+        sweep_local(i)
         if world > 1:
-            gather_async(i, outs[i]["J0"], outs[i]["J1"])
+            tail_async(i)
 
-    def fence():
+    def step_serial():
+        """the same with the tail on the launching stream: the latency of ONE sweep"""
+        sweep_local(0)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            tail(0)
 
-    for _ in range(max(3, a.warmup)):
+    W = max(3, a.warmup)
+    for _ in range(W):
         step()
+    drain()
     fence()
-    launches0 = eng.launch_count
-    ktimes = {}
+    launches0 = eng.launch_count + (eng_tail.launch_count if eng_tail else 0)
     sampler = NvmlSampler(local)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fence()
-    ev0.record()
-    for _ in range(a.steps):
-        step()
-        # per-kernel CUDA-event durations recorded by the library on the launching stream
-        # (read back lazily after the region: the events are only queried here)
-    drain()
-    ev1.record()
-    fence()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = timed_steps(step, a.steps, fence, drain)
     clocks = sampler.stop()
-    launches = eng.launch_count - launches0
-    # per-kernel durations: one extra (untimed) step so the event queries do not perturb the timed region
-    per_kernel_runs = []
+    launches = eng.launch_count + (eng_tail.launch_count if eng_tail else 0) - launches0
+    ms_step = max_over_ranks(ms_total) / a.steps
+    units_total = nR * nE * T
+    units_rank = n_loc * nE * T
+    value = units_total / (ms_step * 1e-3)
+
+    # per-kernel durations (CUDA events recorded by the library on the launching stream): extra untimed steps
+    ktimes, per_kernel_runs = {}, []
+    drain()
     for _ in range(3):
-        step()
+        sweep_local(0)
         torch.cuda.synchronize()
         per_kernel_runs.append(eng.last_kernel_times())
     for k in per_kernel_runs[0]:
         ktimes[k] = float(np.mean([r[k] for r in per_kernel_runs]))
 
+    # N > 1: the serial step and the floor of its tail (all-gather + Pareto alone)
+    strong = None
+    if world > 1:
+        for _ in range(3):
+            step_serial()
+        ms_serial = max_over_ranks(timed_steps(step_serial, a.steps, fence)) / a.steps
+        with torch.cuda.stream(torch.cuda.current_stream()):
+            for _ in range(3):
+                tail(0)
+            ms_tail = max_over_ranks(timed_steps(lambda: tail(0), a.steps, fence)) / a.steps
+        kt_all = [None] * world
+        dist.all_gather_object(kt_all, {k: round(v, 4) for k, v in ktimes.items()})
+        strong = {"ms_per_step_pipelined": ms_step, "ms_per_step_serial": ms_serial,
+                  "collective_and_pareto_floor_ms": ms_tail,
+                  "regions_per_rank": [wl.shard_regions(nR, world, r)[1] - wl.shard_regions(nR, world, r)[0] for r in range(world)],
+                  "tiles_per_rank": (per * nE + 31) // 32,
+                  "kernel_ms_per_rank": kt_all,
+                  "limiter": "the time-sequential passes: ekf_forward walks T days per trajectory with one warp per 32 "
+                             "trajectories, so a shard of %d tiles on 148 SMs is latency- not throughput-bound; the smoother "
+                             "tail (all-gather + Pareto) is the fixed floor" % ((per * nE + 31) // 32)}
+
     # extra (not the headline): the lean sweep mode -- identical outputs, smoother only on the days
     # whose schedule is optimised (include/epi_b200.h: epi_sweep_args.lean)
     ms_lean, lean_same = None, None
-    if not a.no_lean:
-        out_lean = {k: torch.empty_like(v) for k, v in out.items()}
+    if not a.no_lean and world == 1:
+        out_lean = {k: torch.empty_like(v) for k, v in out1.items()}
+        run_lean = lambda: wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
         for _ in range(3):
-            wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
-        fence()
-        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0.record()
-        for _ in range(a.steps):
-            wl.run_sweep(eng, dbatch, None, out=out_lean, lean=True)
-        l1.record()
-        fence()
-        ms_lean = l0.elapsed_time(l1) / a.steps
-        lean_same = all(bool(torch.equal(out_lean[k], out[k])) for k in out)
+            run_lean()
+        ms_lean = timed_steps(run_lean, a.steps, fence) / a.steps
+        lean_same = all(bool(torch.equal(out_lean[k], out1[k])) for k in out1)
 
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / a.steps
-    units_rank = nR * nE * T
-    value = units_rank * world / (ms_step * 1e-3)
-
-    # ---- e2e: the blocking host-memory C-ABI call with pinned host buffers
-    e2e = None
-    if not a.no_e2e:
-        pinned = {}
-        h2d = 0
+    # ---- e2e: the blocking host-memory C-ABI call (H2D + kernels + D2H inside the call), pinned and pageable buffers
+    def e2e_leg(pin):
+        mk = (lambda t: t.pin_memory()) if pin else (lambda t: t)
+        hb, h2d = dict(batch), 0
         for k in wl._SWEEP_ARRAYS:
-            tt = torch.from_numpy(np.ascontiguousarray(batch[k])).pin_memory()
-            pinned[k] = tt.numpy()
+            tt = mk(torch.from_numpy(np.array(batch[k], dtype=np.float64, order="C", copy=True)))
+            hb[k] = tt.numpy()
             h2d += tt.numel() * 8
-        hb = dict(batch)
-        hb.update(pinned)
-        peps = torch.from_numpy(np.ascontiguousarray(eps)).pin_memory().numpy()
+        peps = mk(torch.from_numpy(np.array(eps, dtype=np.float64, copy=True))).numpy()
         h2d += peps.size * 8 + len(bytes(memoryview(batch["prm"])))
-        hout = {"J0": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
-                "J1": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
-                "on_front": torch.empty((nR, nE), dtype=torch.uint8).pin_memory().numpy(),
-                "I_opt": torch.empty((nR,), dtype=torch.int32).pin_memory().numpy()}
-        d2h = sum(v.nbytes for v in hout.values())
-
-        houts = [hout]
-        if world > 1:
-            houts.append({k: torch.from_numpy(np.empty_like(v)).pin_memory().numpy() for k, v in hout.items()})
-            drain()
-            comm_ev[0] = comm_ev[1] = None
+        def hostbufs():
+            o = {"J0": mk(torch.empty((n_loc, nE), dtype=f64)).numpy(), "J1": mk(torch.empty((n_loc, nE), dtype=f64)).numpy()}
+            if world == 1:
+                o["on_front"] = mk(torch.empty((nR, nE), dtype=u8)).numpy()
+                o["I_opt"] = mk(torch.empty((nR,), dtype=i32)).numpy()
+            return o
+        houts = [hostbufs() for _ in range(nbuf)]
+        d2h = sum(v.nbytes for v in houts[0].values())
+        if world > 1:   # the gathered front/knee come back to the host as well
+            hfront = [{"on_front": mk(torch.empty((nR, nE), dtype=u8)), "I_opt": mk(torch.empty((nR,), dtype=i32))}
+                      for _ in range(nbuf)]
+            d2h += nR * nE + nR * 4
+            h2d += 2 * n_loc * nE * 8   # the shard's costs go back up for the NCCL gather
+        drain()
+        for i in range(nbuf):
+            comm_ev[i] = None
         hstep_no = [0]
 
         def step_host():
-            i = hstep_no[0] & 1 if world > 1 else 0
+            i = hstep_no[0] % nbuf
             hstep_no[0] += 1
-            if comm_ev[i] is not None:  # the D2H of this call may overwrite houts[i] only after its last gather
+            if comm_ev[i] is not None:   # the D2H of this call may overwrite houts[i] only after its last tail
                 torch.cuda.current_stream().wait_event(comm_ev[i])
-            wl.run_sweep(eng, hb, peps, out=houts[i])   # blocking: H2D, kernels, D2H, stream sync
+                comm_ev[i].synchronize()
+            wl.run_sweep(eng, hb, peps, out=houts[i], want_front=(world == 1))   # blocking: H2D, kernels, D2H, sync
             if world > 1:
-                gather_async(i, torch.from_numpy(houts[i]["J0"]), torch.from_numpy(houts[i]["J1"]))
+                loc[i]["J0"][:n_loc].copy_(torch.from_numpy(houts[i]["J0"]), non_blocking=True)
+                loc[i]["J1"][:n_loc].copy_(torch.from_numpy(houts[i]["J1"]), non_blocking=True)
+                tail_async(i)
+                with torch.cuda.stream(comm):
+                    hfront[i]["on_front"].copy_(full[i]["on_front"], non_blocking=True)
+                    hfront[i]["I_opt"].copy_(full[i]["I_opt"], non_blocking=True)
+                    comm_ev[i] = torch.cuda.Event()
+                    comm_ev[i].record(comm)
 
         for _ in range(3):
             step_host()
-        fence()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         walls = []
-        for _ in range(a.steps):
+
+        def one():
             tw = time.perf_counter()
             step_host()
             walls.append((time.perf_counter() - tw) * 1e3)
+        ms_e2e = max_over_ranks(timed_steps(one, a.steps, fence, drain)) / a.steps
+        if world == 1:  # parity of the two legs: same bits from the host-memory and device-memory modes
+            assert np.array_equal(houts[0]["J0"], out1["J0"].cpu().numpy()), "host/device legs disagree"
+        return {"value": units_total / (ms_e2e * 1e-3), "unit": "trajectory-days/s",
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                "ms_per_step_median": float(np.median(walls)), "ms_per_step_min": float(min(walls)),
+                "ms_per_step_max": float(max(walls)), "host_buffers": "pinned" if pin else "pageable",
+                "note": "value uses the total over all K steps (one attempt); bytes are this rank's"}
+
+    e2e = e2e_pageable = None
+    if not a.no_e2e:
+        e2e = e2e_leg(True)
+        e2e_pageable = e2e_leg(False)   # what a MATLAB/Octave host hands over (mxGetPr memory is pageable)
+        e2e["pageable"] = {k: e2e_pageable[k] for k in ("value", "ms_per_step", "ms_per_step_median", "ms_per_step_min",
+                                                         "ms_per_step_max")}
+
+    # N > 1 extra: round 1's replicated (weak-scaling) form -- every rank a full 236-region replica
+    replica = None
+    if world > 1 and not a.no_replica:
         drain()
-        e1.record()
-        fence()
-        sys.stderr.write(f"[e2e] per-step wall ms: min {min(walls):.2f} median {float(np.median(walls)):.2f} "
-                         f"max {max(walls):.2f}; kernels {eng.last_kernel_times()}\n")
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ms_e2e = float(te.item()) / a.steps
-        e2e = {"value": units_rank * world / (ms_e2e * 1e-3), "unit": "trajectory-days/s",
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-               "ms_per_step_median": float(np.median(walls)), "ms_per_step_min": float(min(walls)),
-               "ms_per_step_max": float(max(walls)),
-               "note": "value uses the total over all K steps (one attempt)"}
-        # parity of the two legs: same bits from the host-memory and device-memory modes
-        assert np.array_equal(hout["J0"], out["J0"].cpu().numpy()), "host/device legs disagree"
+        inp_r, _ = build_inputs(a, rank)
+        S_r = wl.run_fixed_input(eng, inp_r)
+        db_r = wl.sweep_to_device(wl.sweep_batch(inp_r, S_r), eps, dev)
+        out_r = {"J0": torch.empty((nR, nE), dtype=f64, device=dev), "J1": torch.empty((nR, nE), dtype=f64, device=dev),
+                 "on_front": torch.empty((nR, nE), dtype=u8, device=dev), "I_opt": torch.empty((nR,), dtype=i32, device=dev)}
+        run_r = lambda: wl.run_sweep(eng, db_r, None, out=out_r)
+        for _ in range(3):
+            run_r()
+        k_r = max(3, a.steps // 2)
+        ms_r = max_over_ranks(timed_steps(run_r, k_r, fence)) / k_r
+        replica = {"value": units_total * world / (ms_r * 1e-3), "unit": "trajectory-days/s", "ms_per_step": ms_r,
+                   "scaling": "weak", "note": "every rank sweeps its own 236-region replica; no collective in the step"}
+        del db_r, out_r
+        torch.cuda.empty_cache()
+        eng.release_cache()
 
     # ---- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -466,23 +557,27 @@ def main():
                    "hbm_gbs": ab * units_rank / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
                    "fp64_tflops": fl * units_rank / (ms * 1e-3) / 1e12 if ms > 0 else 0.0}
     achieved = kern[dom]["hbm_gbs"]
-    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    traffic, traffic_src = None, None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
     try:
-        if (a.regions, a.eps, a.t_hist, a.t_fore) == (236, 250, 441, 120):
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom]["traffic"]
+        if (a.regions, a.eps, a.t_hist, a.t_fore, world) == (236, 250, 441, 120, 1):
+            for name in ("r02_traffic.json", "r01_traffic.json"):
+                tp = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(tp) and dom in json.load(open(tp)):
+                    traffic, traffic_src = json.load(open(tp))[dom]["traffic"], f"profiles/{name} (ncu --set full, per launch)"
+                    break
     except Exception:
         traffic = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_source": "profiles/r01_traffic.json (ncu --set full, per launch)" if traffic else None,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": KERNEL_ALGO[dom][0] * units_rank, "peak_source": peak_src,
                 "algorithmic_bytes_per_trajectory_day": KERNEL_ALGO[dom][0],
                 "fp64": {"achieved_tflops": kern[dom]["fp64_tflops"], "peak_tflops_measured": fp64_tflops,
                          "frac": kern[dom]["fp64_tflops"] / fp64_tflops if fp64_tflops else None,
                          "canonical_flops_per_trajectory_day": KERNEL_ALGO[dom][1]},
-                "step": {"hbm_frac": BYTES_FUSED_M6 * units_rank / (ms_step * 1e-3) / 1e9 / hbm_peak,
-                         "fp64_frac": FLOPS_EKF_EKS_M6 * units_rank / (ms_step * 1e-3) / 1e12 / fp64_tflops
-                         if fp64_tflops else None},
+                "step": {"hbm_frac": BYTES_FUSED_M6 * units_total / world / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                         "fp64_frac": FLOPS_EKF_EKS_M6 * units_total / world / (ms_step * 1e-3) / 1e12 / fp64_tflops
+                         if fp64_tflops else None,
+                         "note": "per GPU: canonical work of the whole job / N / step time"},
                 "kernels": kern}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only)
@@ -513,23 +608,40 @@ def main():
                                      "what": "NumPy twin of the same .m files (interpreter regime; EKF/EKS only)",
                                      "sample": f"{n_tw} trajectories x {T} days, {tw_dt:.2f} s"},
                "sample": f"{n} of {nR} regions x {nE} eps x {T} days, {dt:.1f} s (C oracle, OpenMP)",
-               "parity_with_gpu_bit_exact": bool(np.array_equal(j0, out["J0"].cpu().numpy()[:n]) and
-                                                 np.array_equal(j1, out["J1"].cpu().numpy()[:n]))}
+               "parity_with_gpu_bit_exact": bool(np.array_equal(j0, out1["J0"].cpu().numpy()[:n]) and
+                                                 np.array_equal(j1, out1["J1"].cpu().numpy()[:n]))}
+
+    # ---- the other BASELINE configs (2, 3, 5), outside the headline timing: ms, rate, roofline fraction and an
+    # oracle spot check each (tools/bench_configs.py)
+    secondary = None
+    if rank == 0 and world == 1 and not a.no_secondary:
+        try:
+            del dbatch
+            torch.cuda.empty_cache()
+            eng.release_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            secondary = bench_configs.measure(eng, spot_check=True, fp64=fp64_tflops)
+        except Exception as exc:  # the headline line must still be printed
+            secondary = {"error": repr(exc)}
 
     if rank == 0:
+        par = ("1 GPU: the whole sweep, Pareto inside epi_sweep" if world == 1 else
+               f"strong: {nR} regions sharded in contiguous blocks of {per} over {world} GPUs; per step ONE all-gather of the "
+               "per-shard (J0,J1) (two NCCL calls, J0 and J1) then the Pareto step on the gathered costs, on a side stream "
+               "overlapping the next step's sweep and drained inside the timed region")
         line = {"metric": "trajectory_days_per_sec", "value": value, "unit": "trajectory-days/s", "n_gpus": world,
-                "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "trajectories_per_gpu": nR * nE, "days": T,
-                           "parallelism": f"regions replicated per GPU x{world} (weak); one all-gather of (J0,J1) per step on a side "
-                                          "stream, overlapping the next step's sweep, drained inside the timed region",
-                           "l2": "per-step tape traffic (>30 GB) far exceeds the 126 MB L2; no explicit flush",
+                "steps": a.steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "trajectories_total": nR * nE, "trajectories_this_gpu": n_loc * nE,
+                           "days": T, "parallelism": par,
+                           "l2": "per-step tape traffic (>30 GB at N = 1, >3 GB per GPU at N = 8) far exceeds the 126 MB L2; no explicit flush",
                            "mode_value": "EPI_MEM_DEVICE (inputs resident in HBM)",
-                           "mode_e2e": "EPI_MEM_HOST (pinned host buffers, blocking call)"},
+                           "mode_e2e": "EPI_MEM_HOST (host buffers, blocking call; pinned = headline, pageable beside it)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "strong_scaling": strong, "replica_weak": replica, "secondary": secondary,
                 "lean_mode": None if ms_lean is None else {
-                              "value": units_rank * world / (ms_lean * 1e-3), "unit": "trajectory-days/s",
+                              "value": units_total / (ms_lean * 1e-3), "unit": "trajectory-days/s",
                               "ms_per_step": ms_lean, "outputs_bit_identical_to_full": lean_same,
                               "note": "not the headline: smoother gains/backward only on the days to optimise "
                                       "(epi_sweep_args.lean); same J0/J1/front/knee bits"}}
@@ -537,6 +649,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if eng_tail:
+        eng_tail.close()
     eng.close()
     return 0
 

@@ -25,23 +25,22 @@ import numpy as np
 from . import _capi as K
 from .engine import Engine, pack_params
 
-_engine = None
+_engines = {}
 
 
 def get_engine(device=0):
-    """Process-wide engine (one context per host thread / GPU)."""
-    global _engine
-    if _engine is None:
-        _engine = Engine(device)
-        atexit.register(_close_engine)
-    return _engine
+    """Process-wide engine of GPU `device` (one context per host thread / GPU)."""
+    device = int(device)
+    if device not in _engines:
+        if not _engines:
+            atexit.register(_close_engine)
+        _engines[device] = Engine(device)
+    return _engines[device]
 
 
 def _close_engine():
-    global _engine
-    if _engine is not None:
-        _engine.close()
-        _engine = None
+    for dev in list(_engines):
+        _engines.pop(dev).close()
 
 
 def _K_of(T, dt):

@@ -267,6 +267,10 @@ class Engine:
     def random_schedules(self, prm, B, K_, L, G, seed, first=0, device=False):
         """The schedules EPI_U_PHILOX integrates, written out: uint8 [K,L,B]."""
         mem = K.MEM_DEVICE if device else K.MEM_HOST
+        if device:
+            # device-memory calls run on torch's CURRENT stream (see _mode): the output tensor and the
+            # temporary params tensor belong to it, so the kernel must be ordered on it too
+            self.use_torch_stream()
         a = K.SchedulesArgs()
         a.mem, a.B, a.K, a.L, a.G = mem, int(B), int(K_), int(L), int(G)
         a.prm = self._prm(prm, mem)
@@ -441,16 +445,22 @@ class Engine:
         return res
 
     # -- Pareto -------------------------------------------------------------------
-    def pareto(self, J0, J1):
-        """TrainPredictPrescribeNPI.m:624-633 for n_sets point sets: J0, J1 [n_sets, n]."""
+    def pareto(self, J0, J1, out=None):
+        """TrainPredictPrescribeNPI.m:624-633 for n_sets point sets: J0, J1 [n_sets, n].
+        `out` = (on_front uint8 [n_sets, n], I_opt int32 [n_sets]) reuses preallocated device buffers."""
         mem = self._mode(J0, J1)
         n_sets, n = (int(v) for v in J0.shape)
         a = K.ParetoArgs()
         a.mem, a.n_sets, a.n = mem, n_sets, n
         a.J0 = self._in(J0, mem, n=n_sets * n)
         a.J1 = self._in(J1, mem, n=n_sets * n)
-        mask, a.on_front = self._out((n_sets, n), mem, dtype=np.uint8)
-        iopt, a.I_opt = self._out((n_sets,), mem, dtype=np.int32)
+        if out is not None and mem == K.MEM_DEVICE:
+            mask, iopt = out
+            a.on_front = self._in(mask, mem, dtype=np.uint8, n=n_sets * n)
+            a.I_opt = self._in(iopt, mem, dtype=np.int32, n=n_sets)
+        else:
+            mask, a.on_front = self._out((n_sets, n), mem, dtype=np.uint8)
+            iopt, a.I_opt = self._out((n_sets,), mem, dtype=np.int32)
         try:
             self._ck(self._lib.epi_pareto_batch(self._h, C.byref(a)))
         finally:
@@ -494,8 +504,14 @@ class Engine:
 
         def outbuf(name, shape, dtype=np.float64):
             if name in out:
-                res[name] = out[name]
-                return self._in(out[name], mem, dtype=dtype, n=int(np.prod(shape)))
+                o = out[name]
+                if mem == K.MEM_HOST:
+                    # the result is written through this pointer: never hand the library a converted copy
+                    if not (isinstance(o, np.ndarray) and o.flags["C_CONTIGUOUS"] and o.flags["WRITEABLE"]
+                            and o.dtype == np.dtype(dtype)):
+                        raise ValueError(f"out[{name!r}] must be a writeable C-contiguous {np.dtype(dtype)} array")
+                res[name] = o
+                return self._in(o, mem, dtype=dtype, n=int(np.prod(shape)))
             res[name], ptr = self._out(shape, mem, dtype=dtype)
             return ptr
 

@@ -40,16 +40,27 @@ def timed(fn, reps=5, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--scale", type=float, default=1.0)
-    ap.add_argument("--only", type=int, default=0, help="run a single config (2, 3 or 5)")
-    a = ap.parse_args()
-    eng = Engine(0)
+def _orc():
+    from oracle import oracle as orc   # the checker (test infrastructure): spot checks only
+    return orc
+
+
+def _bits(a, b):
+    return bool(np.array_equal(np.asarray(a), np.asarray(b)))
+
+
+def measure(eng, only=0, scale=1.0, spot_check=True, fp64=None):
+    """Time configs 2, 3 and 5 on the engine's device; returns a list of records.  With
+    `spot_check` a handful of trajectories of every config is compared bit for bit with the
+    CPU oracle (outside the timed calls)."""
+    class A:
+        pass
+    a = A()
+    a.scale, a.only = scale, only
     eng.use_torch_stream()
-    fp64 = eng.fp64_probe(4096)
+    fp64 = fp64 or eng.fp64_probe(4096)
     out = []
-    dev = "cuda:0"
+    dev = f"cuda:{eng.device}"
 
     nR = 236
     holder = {}
@@ -69,6 +80,16 @@ def main():
                    "fp64_tflops": 37.0 * steps / ms * 1e3 / 1e12}
             rec["hbm_frac"] = rec["hbm_gbs"] / HBM
             rec["fp64_frac"] = rec["fp64_tflops"] / fp64
+            if spot_check and mode == K.SEIRP_OUT_FULL:
+                o, full = _orc(), eng.seirp(rd, icd, Kn, 1.0, out_mode=mode)
+                eng.sync()
+                ok = True
+                for b in (0, 31, B // 2, B - 1):
+                    want = o.SEIRP(*rates[:, b], *ic[:, b], float(Kn), 1.0)
+                    got = full[:, :, b].cpu().numpy()
+                    ok = ok and all(_bits(got[f], want[f][0]) for f in range(5))
+                rec["oracle_spot_check"] = {"trajectories": 4, "bit_exact": ok}
+                del full
             out.append(rec)
         del rd, icd
         sat = dict(beta_0=0.1, beta_s=0.01, mu_0=0.02, mu_s=0.2, sigma=1.0, i_0=0.1)
@@ -109,7 +130,19 @@ def main():
         eng.set_scratch_limit(0)
         kt = eng.last_kernel_times()
         units = Bt * T
-        out.append({"config": 3, "kernel": "ekf_eks<3> lean (S_SMOOTH out)", "B": Bt, "T": T, "ms": ms,
+        spot3 = None
+        if spot_check:
+            o, S, ok = _orc(), holder["o"]["S_SMOOTH"], True
+            picks = (0, nRep - 1, nRep, Bt // 2 + 7, Bt - 1)
+            for bb in picks:
+                r = inp[bb // nRep]
+                s3 = r["setup3"]
+                want = o.ekf_eks(o.SIALPHA, r["u_fixed"], x[:, bb].cpu().numpy(), s3["params"], s3["s_init"], s3["Ps_init"],
+                                 s3["s_final"], s3["Ps_final"], s3["w_bar"], 0.0, s3["Q_w"], r["R_v"], 1.0, s3["gamma_ekf"],
+                                 s3["W"], 1)
+                ok = ok and _bits(S[:, :, bb].cpu().numpy().T, want["S_SMOOTH"])
+            spot3 = {"trajectories": len(picks), "bit_exact": ok}
+        out.append({"config": 3, "oracle_spot_check": spot3, "kernel": "ekf_eks<3> lean (S_SMOOTH out)", "B": Bt, "T": T, "ms": ms,
                     "trajectory_days_per_s": units / ms * 1e3, "kernel_ms": kt, "kernel_ms_sum": sum(kt.values()),
                     "hbm_gbs_algorithmic(616B)": 616.0 * units / ms * 1e3 / 1e9,
                     "hbm_frac": 616.0 * units / ms * 1e3 / 1e9 / HBM,
@@ -124,22 +157,15 @@ def main():
         nS, Kn, L = int(100_000 * a.scale), 120, 12
         reg = syn.load_regions(nR)
         Bm = nR * nS
-        umax = torch.tensor(reg["npi_max"], dtype=torch.float64, device=dev)
-        u8 = torch.empty((Kn, L, Bm), dtype=torch.uint8, device=dev)
-        g = torch.Generator(device=dev).manual_seed(5)
-        for j in range(L):  # TrainPredictPrescribeNPI.m:500-510: first half constant in time, second half per day
-            hi = int(reg["npi_max"][j]) + 1
-            per_day = torch.randint(0, hi, (Kn, Bm), dtype=torch.uint8, device=dev, generator=g)
-            const = torch.randint(0, hi, (1, Bm), dtype=torch.uint8, device=dev, generator=g)
-            first_half = (torch.arange(Bm, device=dev) % nS) < (nS // 2)
-            u8[:, j, :] = torch.where(first_half[None, :], const.expand(Kn, Bm), per_day)
-            del per_day, const
         prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
                                 u_min=np.zeros(L), alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
         x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(nR)]))
         w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(nR)]))
         j0p, j1p = torch.zeros(nR, dtype=torch.float64, device=dev), torch.zeros(nR, dtype=torch.float64, device=dev)
         prmd = params_to_device(prm, dev)
+        # the schedules of TrainPredictPrescribeNPI.m:500-510 (first half of a region's scenarios constant in time,
+        # second half per day), written out as uint8 by the library's counter-based rule (seed 5)
+        u8 = eng.random_schedules(prmd, Bm, Kn, L, nS, 5, device=True)
 
         def run5():
             holder["o"] = eng.rollout_cost(prmd, x0, u8, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True,
@@ -147,7 +173,20 @@ def main():
         ms_call = timed(run5, reps=3, warm=1)
         ms = sum(eng.last_kernel_times().values())
         units = Bm * Kn
-        out.append({"config": 5, "kernel": "rollout_cost[u8]", "B": Bm, "K": Kn, "ms": ms,
+        spot5 = None
+        if spot_check:
+            o, ok = _orc(), True
+            x0h, wh = x0.cpu().numpy(), w.cpu().numpy()
+            picks = (0, nS - 1, nS, Bm // 2 + 3, Bm - 1)
+            for bb in picks:
+                r = bb // nS
+                ub = u8[:, :, bb].cpu().numpy().T.astype(float)
+                s_, i_, al_ = o.SIalpha_Controlled(ub, *x0h[r], reg["npi_max"], 1e-8, 100.0, syn.GAMMA, reg["a"][r], reg["b"][r],
+                                                   syn.BETA, 0.0, 0.0, 0.0, Kn, 1.0)
+                j0, j1 = o.NPICost((s_ * i_) * al_, ub, wh[r].T)
+                ok = ok and float(holder["o"]["J0"][bb]) == j0 and float(holder["o"]["J1"][bb]) == j1
+            spot5 = {"trajectories": len(picks), "bit_exact": bool(ok)}
+        out.append({"config": 5, "kernel": "rollout_cost[u8]", "oracle_spot_check": spot5, "B": Bm, "K": Kn, "ms": ms,
                     "trajectory_days_per_s": units / ms * 1e3, "hbm_gbs_algorithmic(12B)": 12.0 * units / ms * 1e3 / 1e9,
                     "hbm_frac": 12.0 * units / ms * 1e3 / 1e9 / HBM, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64})
 
@@ -161,15 +200,11 @@ def main():
                                            T_total=Kn, j0_prefix=j0p, j1_prefix=j1p, w=w, seed=5)
         timed(run5g, reps=3, warm=1)
         ms = sum(eng.last_kernel_times().values())
-        ug = eng.random_schedules(prmd, Bm, Kn, L, nS, 5, device=True)
-        chk = eng.rollout_cost(prmd, x0, ug, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True, T_total=Kn,
-                               j0_prefix=j0p, j1_prefix=j1p, w=w)
         eng.sync()
-        same = bool(torch.equal(chk["J0"], holder["g"]["J0"]) and torch.equal(chk["J1"], holder["g"]["J1"]))
+        same = bool(torch.equal(holder["o"]["J0"], holder["g"]["J0"]) and torch.equal(holder["o"]["J1"], holder["g"]["J1"]))
         out.append({"config": 5, "kernel": "rollout_cost[philox, generated in-kernel]", "B": Bm, "K": Kn, "ms": ms,
                     "trajectory_days_per_s": units / ms * 1e3, "fp64_frac(91flop)": 91.0 * units / ms * 1e3 / 1e12 / fp64,
                     "bit_identical_to_supplied_u8": same})
-        del ug, chk
         holder["o"] = holder["g"]
 
         J0, J1 = holder["o"]["J0"].view(nR, nS), holder["o"]["J1"].view(nR, nS)
@@ -178,10 +213,25 @@ def main():
         out.append({"config": 5, "kernel": "pareto[sorted]", "n_sets": nR, "n": nS, "ms": ms,
                     "points_per_s": nR * nS / ms * 1e3, "front_sizes_mean": float(mask.sum(dim=1).double().mean().item())})
 
+    for r in out:
+        r["hbm_peak_gbs"], r["fp64_peak_tflops_measured"] = HBM, fp64
+    holder.clear()
+    torch.cuda.empty_cache()
+    eng.release_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--only", type=int, default=0, help="run a single config (2, 3 or 5)")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle spot checks")
+    a = ap.parse_args()
+    eng = Engine(0)
+    out = measure(eng, a.only, a.scale, spot_check=not a.no_check)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "configs.jsonl"), "w") as f:
         for r in out:
-            r["hbm_peak_gbs"], r["fp64_peak_tflops_measured"] = HBM, fp64
             f.write(json.dumps(r) + "\n")
             print(json.dumps(r))
     eng.close()
