@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
   const int k = k0 + (int)(tid / Bpad);
   const int b = (int)(tid % Bpad);
 #endif
+  // lanes of this warp that hold a trajectory (the pair-at-a-time pinv is warp-synchronous)
+  const unsigned wmask = __ballot_sync(0xffffffffu, b < P.B);
   if (b >= P.B) return;
   const int pos = REV ? (T - 1 - k) : k;
   const int posn = REV ? (T - 2 - k) : (k + 1);
@@ -92,6 +94,26 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
     }
 #pragma unroll
     for (int q = 0; q < Mat<M, true>::N; ++q) bad |= !(fabs(Pn.v[q]) <= 1.79769313486231570815e308);  // :211
+#if EPI_PINV_MODE == 4 && !defined(EPI_GAIN_SKIP_PINV)
+    if constexpr (M == 6) {
+      // the matrix goes to this thread's shared-memory column; every lane of the warp enters, a guarded
+      // (non-finite) matrix takes no rotation
+      double *col = rot_stack + threadIdx.x;
+#pragma unroll
+      for (int q = 0; q < 21; ++q) col[q * EPI_GAIN_BLOCK] = Pn.v[q];
+      rank = pinv_sym6_smem<EPI_GAIN_BLOCK>(col, wmask, bad);
+#pragma unroll
+      for (int q = 0; q < 21; ++q) X.v[q] = col[q * EPI_GAIN_BLOCK];
+      if (bad) rank = M;
+    }
+#endif
+#if (EPI_PINV_MODE == 3 || EPI_PINV_MODE == 5) && !defined(EPI_GAIN_SKIP_PINV)
+    if constexpr (M == 6) {
+      // every lane of the warp enters; a guarded (non-finite) matrix takes no rotation
+      rank = pinv_sym6_pairs<EPI_GAIN_BLOCK, EPI_PINV_MODE == 5>(Pn, X, rot_stack + threadIdx.x, wmask, bad);
+      if (bad) rank = M;
+    }
+#endif
     if (bad) {
 #pragma unroll
       for (int q = 0; q < MM; ++q) Jm.v[q] = 0.0;  // :213
@@ -99,7 +121,10 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
 #ifdef EPI_GAIN_SKIP_PINV  // experiment: cost of everything but the eigen-iteration
       X = Pn;
 #else
-      rank = pinv_sym<M, EPI_GAIN_BLOCK>(Pn, X, rot_stack + threadIdx.x);
+      if (!(EPI_PINV_MODE >= 3 && M == 6)) rank = pinv_sym<M, EPI_GAIN_BLOCK>(Pn, X, rot_stack + threadIdx.x);
+#endif
+#ifdef EPI_GAIN_PHASE_SYNC
+      __syncthreads();
 #endif
       // the state Jacobian is evaluated AFTER the eigen-iteration so that neither its entries nor
       // the model constants are live (or spilled) across it
@@ -196,7 +221,18 @@ static void launch_gain_model(const EkfParams &p, cudaStream_t st) {
   const int block = EPI_GAIN_BLOCK;
   const unsigned grid = (unsigned)((total + block - 1) / block);
   constexpr int M = model_dim(MODEL);
-  const size_t smem = model_legacy(MODEL) ? 0 : sizeof(double) * RotStack<M, EPI_GAIN_BLOCK>::SMEM_WORDS;
+#if EPI_PINV_MODE == 4
+  constexpr size_t words6 = SmemPinv6<EPI_GAIN_BLOCK>::SMEM_WORDS;
+#elif EPI_PINV_MODE == 5
+  constexpr size_t words6 = RotStackU<EPI_GAIN_BLOCK>::SMEM_WORDS + 21 * EPI_GAIN_BLOCK;
+#elif EPI_PINV_MODE == 3
+  constexpr size_t words6 = RotStackU<EPI_GAIN_BLOCK>::SMEM_WORDS;
+#elif EPI_PINV_MODE == 0
+  constexpr size_t words6 = RotStack<6, EPI_GAIN_BLOCK>::SMEM_WORDS;
+#else
+  constexpr size_t words6 = RotStackSel<6, EPI_GAIN_BLOCK>::SMEM_WORDS;
+#endif
+  const size_t smem = model_legacy(MODEL) ? 0 : sizeof(double) * (M == 6 ? words6 : (size_t)RotStack<M, EPI_GAIN_BLOCK>::SMEM_WORDS);
   if (p.tiled) {
     cudaFuncSetAttribute(eks_gain_kernel<MODEL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     eks_gain_kernel<MODEL, true><<<grid, block, smem, st>>>(p);

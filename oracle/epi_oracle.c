@@ -260,10 +260,10 @@ static void jacobi_angle(double app, double aqq, double apq, double *t_, double 
  * (column-major mxm), pairs in the set order above.  A pair (p,q) is ACTIVE iff
  * |a_pq| > 2^-62 * max_p|a_pp| (threshold recomputed at each sweep start); the
  * iteration stops when no pair is active at a sweep start (or after 16 sweeps).
- * Idle pairs are SKIPPED (no arithmetic touches their rows/columns); the angles
- * of a set's active pairs read disjoint entries, so they are all taken from the
- * matrix as it stands when the set starts and the rotations are then applied
- * in the listed order.  lambda_i = diagonal after convergence; the eigenvector matrix
+ * A set with no active pair is skipped; in an executed set every pair is
+ * rotated, the idle ones by the identity (t = 0, c = 1, s = 0) -- that changes
+ * no value (at most the sign of a zero) and makes the set branch-free in the
+ * kernel.  lambda_i = diagonal after convergence; the eigenvector matrix
  * V = R_1 R_2 ... R_n (R_k: plane rotation with R_pp = R_qq = c, R_pq = s,
  * R_qp = -s) is never formed:
  *   pinv = V W V' = R_1 ( ... (R_n W R_n') ... ) R_1',   W = diag([|lambda_i| > tol] / lambda_i),
@@ -299,13 +299,12 @@ int orc_pinv_sym(const double *Ain, int m, double *X, int *rank) {
       }
       if (!any_act) continue;
       for (int i = 0; i < n_set; ++i) {
-        if (!act[i]) continue; /* idle pair: skipped */
         const int p = sets[st * n_set + i][0], q = sets[st * n_set + i][1];
         const double t = tt[i], c = cc[i], s = ss[i];
         double app = a[p][p], aqq = a[q][q], apq = a[p][q];
         a[p][p] = app - t * apq;
         a[q][q] = aqq + t * apq;
-        a[p][q] = 0.0; a[q][p] = 0.0;
+        if (act[i]) { a[p][q] = 0.0; a[q][p] = 0.0; }
         for (int r = 0; r < m; ++r) {
           if (r != p && r != q) {
             double g = a[r][p], h = a[r][q];

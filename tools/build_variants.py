@@ -12,6 +12,9 @@ for spec in sys.argv[1:]:
     lib = _build.build(force=True, extra_flags=[f for f in flags.split(",") if f], lib=os.path.join(d, "libepi_b200.so"),
                        obj_dir=os.path.join(d, "build"))
     log = open(os.path.join(d, "build", "eks_gain.o.log")).read()
+    for f in os.listdir(os.path.join(d, "build")):   # the objects are not needed on the GPU box (snapshot size limit)
+        if f.endswith(".o"):
+            os.remove(os.path.join(d, "build", f))
     import re
     for m in re.finditer(r"Function properties for (\S*eks_gain_kernelILi2ELb1E\S*)\n\s*(.*)\nptxas info\s*: Used (\d+) registers", log):
         print(name, m.group(2).strip(), "regs", m.group(3))

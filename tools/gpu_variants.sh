@@ -1,7 +1,7 @@
 # usage: bash tools/gpu_variants.sh v0 v1 ...   (libraries built by tools/build_variants.py)
 for v in "$@"; do
   export EPI_B200_LIB=$PWD/epidemicmodeling_b200/variants/$v/libepi_b200.so
-  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-lean > gpurun_out/var_$v.log 2> gpurun_out/var_$v.err
+  python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-lean --no-secondary > gpurun_out/var_$v.log 2> gpurun_out/var_$v.err
   python - <<PY
 import json
 try:
