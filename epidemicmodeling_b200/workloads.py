@@ -50,15 +50,21 @@ def run_fixed_input(engine, inputs):
     return out["S_SMOOTH"]
 
 
-def sweep_batch(inputs, S_SMOOTH_fixed):
+def sweep_batch(inputs, S_SMOOTH_fixed, x0=None):
     """Per-region arrays of Engine.sweep from the synthetic inputs and the
-    fixed-input smoothed states [T,3,nR] (:380-382 historic estimates, :481 start)."""
+    fixed-input smoothed states [T,3,nR] (:380-382 historic estimates, :481 start).
+    `x0` [nR,3] overrides the rollout start; it is REQUIRED when there is no historic day
+    (the reference takes the start from the last historic day, :481)."""
     L = inputs[0]["u_hist"].shape[0]
     T, Th = inputs[0]["T"], inputs[0]["T_hist"]
     S = np.asarray(S_SMOOTH_fixed)
     hist = S[:Th]                                             # [Th,3,nR]
     newcases_hist = ((hist[:, 0] * hist[:, 1]) * hist[:, 2]).T  # s.*i.*alpha  [nR,Th]
-    x0 = hist[Th - 1].T                                       # [nR,3]
+    if x0 is None:
+        if Th < 1:
+            raise ValueError("sweep_batch: no historic day to start the rollout from -- pass x0")
+        x0 = hist[Th - 1].T                                   # [nR,3]
+    x0 = np.asarray(x0, dtype=np.float64)
     u = np.stack([np.concatenate([np.ascontiguousarray(r["u_hist"].T), np.full((T - Th, L), np.nan)])
                   for r in inputs])                           # :458
     return dict(

@@ -632,16 +632,84 @@ def test_sweep_matches_oracle_and_golden(engine):
 
 @pytest.mark.parametrize("T_hist,T_fore", [(0, 25), (25, 0), (1, 1), (40, 1)])
 def test_sweep_lean_edge_shapes(engine, T_hist, T_fore):
-    """No history / no forecast / single days: lean == full."""
-    if T_hist == 0:
-        pytest.skip("the fixed-input smoother needs at least one historic day")
+    """No history / no forecast / single days: lean == full, and == the oracle.  With no history there is no
+    fixed-input smoother to start the rollout from (TrainPredictPrescribeNPI.m:481 indexes the last historic
+    day): the caller supplies the start state and an empty new-case history."""
     inp, eps = cases.sweep_case(n_regions=2, n_eps=5, T_hist=T_hist, T_fore=T_fore)
-    S = wl.run_fixed_input(engine, inp)
-    batch = wl.sweep_batch(inp, S)
+    if T_hist == 0:
+        x0 = np.stack([r["setup6"]["s_init"][:3] for r in inp])
+        S = np.zeros((T_fore, 3, len(inp)))
+        batch = wl.sweep_batch(inp, S, x0=x0)
+    else:
+        S = wl.run_fixed_input(engine, inp)
+        batch = wl.sweep_batch(inp, S)
     full = wl.run_sweep(engine, batch, eps)
     lean = wl.run_sweep(engine, batch, eps, lean=True)
     for k in ("J0", "J1", "on_front", "I_opt"):
         assert_bits(lean[k], full[k], f"lean {k} T_hist={T_hist} T_fore={T_fore}")
+    o = orc()
+    for r, rin in enumerate(inp):
+        s6 = rin["setup6"]
+        reg = o.SweepRegion(s6["params"], rin["T"], T_hist, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                            s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21,
+                            batch["x0"][r, 0], batch["x0"][r, 1], batch["x0"][r, 2], batch["newcases_hist"][r],
+                            rin["weights"])
+        j0, j1, m, io, _ = o.sweep_region(reg, eps)
+        assert_bits(full["J0"][r], j0, f"J0 T_hist={T_hist} T_fore={T_fore}")
+        assert_bits(full["J1"][r], j1, f"J1 T_hist={T_hist} T_fore={T_fore}")
+        assert np.array_equal(full["on_front"][r].astype(bool), m) and full["I_opt"][r] == io
+
+
+def _guard_case(name):
+    """6-state inputs that drive P_MINUS out of the well-behaved regime (GenericExtendedKalmanFilter.m:209-215)."""
+    c = cases.ekf6_case(0, T_hist=30, T_fore=12)
+    z = np.zeros((6, 6))
+    if name == "overflow":      # covariances overflow to Inf on day 5: the isnan/isinf guard sets J = 0
+        c.update(Ps_init=np.eye(6) * 1e306, Q_w=np.eye(6) * 1e307)
+    elif name == "infQ":        # an infinite process-noise entry: guard from the first day on
+        c.update(Q_w=np.diag([1e-6, 1e-6, np.inf, 1e-6, 1e-6, 1e-6]))
+    elif name == "zero":        # P_MINUS == 0: pinv of the zero matrix, rank 0
+        c.update(Ps_init=z.copy(), Q_w=z.copy())
+    elif name == "rank1":       # rank-1 covariance, no process noise: rank 1 on every day
+        e = z.copy(); e[1, 1] = 1e-4
+        c.update(Ps_init=e, Q_w=z.copy())
+    elif name == "rank2q":      # rank grows 2 -> 4 -> 5 and stays deficient
+        c.update(Ps_init=z.copy(), Q_w=np.diag([1e-8, 1e-8, 0, 0, 0, 0.0]))
+    return c
+
+
+@pytest.mark.parametrize("name", ["overflow", "infQ", "zero", "rank1", "rank2q"])
+def test_smoother_guard_and_rank_deficit(engine, name):
+    """The P_MINUS NaN/Inf guard (J = 0, :209-214) and rank-deficient pinv (:215): same bits as the oracle
+    (NaN positions included) and the status word reports both -- (6 - min rank) << 8 | guard-hit."""
+    c = _guard_case(name)
+    eps = np.array([1e-6, 0.3, 0.9])
+    T, L = c["u"].shape[1], 12
+    cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+    out = engine.ekf_eks(K.MODEL_OPTCTRL, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], c["R_v"],
+                         cm(c["Q_w"]), c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]),
+                         B=eps.size, T=T, L=L, G=eps.size, epsilon=eps, r_mode=K.R_PERDAY, fixed_R=False,
+                         beta=1.0, gamma=0.995, W=21, want_status=True)
+    o = orc()
+    seen_guard = seen_deficit = False
+    for e, ev in enumerate(eps):
+        cc = dict(c, params=dict(c["params"], epsilon=ev))
+        with np.errstate(all="ignore"):
+            want = o.ekf_eks(o.OPTCTRL, *ekf_args(cc))
+        for k in ("S_PLUS", "S_SMOOTH", "u_opt", "u_opt_smooth"):
+            assert_bits(out[k][:, :, e].T, want[k], f"{name} eps={ev} {k}")
+        assert_bits(out["P_SMOOTH"][:, :, e].reshape(T, 6, 6).transpose(2, 1, 0), want["P_SMOOTH"], f"{name} P_SMOOTH")
+        status = 0
+        for k in range(1, T):
+            Pm = want["P_MINUS"][:, :, k]
+            if not np.all(np.isfinite(Pm)):
+                status = max(status, 1)
+            else:
+                status = max(status, (6 - o.pinv_sym(Pm)[1]) << 8)
+        assert int(out["status"][e]) == status, (name, ev, int(out["status"][e]), status)
+        seen_guard |= bool(status & 1)
+        seen_deficit |= bool(status >> 8)
+    assert seen_guard == (name in ("overflow", "infQ")) and seen_deficit == (name in ("zero", "rank1", "rank2q"))
 
 
 @pytest.mark.parametrize("segments", [2, 5, 64])
