@@ -137,6 +137,7 @@ SYMBOLS = {
     "epi_ekf_eks_batch": (C.c_int, [C.c_void_p, C.POINTER(EkfArgs)]),
     "epi_pareto_batch": (C.c_int, [C.c_void_p, C.POINTER(ParetoArgs)]),
     "epi_sweep": (C.c_int, [C.c_void_p, C.POINTER(SweepArgs)]),
+    "epi_sweep_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(SweepArgs)]),
 }
 
 _lib = None

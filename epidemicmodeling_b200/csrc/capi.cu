@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <chrono>
 #include <vector>
+#include <thread>
+#include <algorithm>
 
 #include "epi_device.cuh"
 #include "epi_internal.h"
@@ -254,8 +256,20 @@ long long plan_wave(epi_ctx *c, long long B, size_t per) {
 template <class F>
 int guarded(epi_ctx *ctx, F &&f) {
   if (!ctx) return EPI_ERR_ARG;
+  // the calling thread's current device is the host framework's business (torch tracks it per thread):
+  // switch to the context's GPU for the call and put the caller's back afterwards
+  struct DeviceScope {
+    int prev = -1, mine;
+    explicit DeviceScope(int dev) : mine(dev) {
+      if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+      if (prev != mine) CK(cudaSetDevice(mine));
+    }
+    ~DeviceScope() {
+      if (prev >= 0 && prev != mine) cudaSetDevice(prev);
+    }
+  };
   try {
-    CK(cudaSetDevice(ctx->device));
+    DeviceScope scope(ctx->device);
     f();
     ctx->err.clear();
     return EPI_OK;
@@ -1163,4 +1177,92 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     finish(c, a->mem);
     tr.mark("sync");
   });
+}
+
+// -------------------------------------------------------------------------------------------------
+// epi_sweep_multi: the region-sharded sweep on several GPUs from ONE blocking host call
+// (Tools/TrainPredictPrescribeNPI.m:93 is the region loop, :421 the epsilon loop).  Regions are independent
+// (SURVEY 8e), so shard i -- a contiguous block of regions -- is one epi_sweep on context i, driven by its
+// own host thread; every per-region input of epi_sweep_args is region-major, so a shard's arguments are the
+// caller's pointers advanced to its first region, and J0/J1/front/knee land directly in the caller's rows:
+// the "gather" of a single-process host is the D2H copy of each shard.  The three trajectory-minor arrays
+// (noise in, u_fore / P_first out: [..][B]) go through per-shard staging buffers.
+namespace {
+struct ShardPlan { int lo, hi; };
+ShardPlan shard_of(int n_regions, int n_shards, int i) {
+  const int per = (n_regions + n_shards - 1) / n_shards;
+  ShardPlan s;
+  s.lo = std::min(n_regions, i * per);
+  s.hi = std::min(n_regions, s.lo + per);
+  return s;
+}
+}  // namespace
+
+extern "C" int epi_sweep_multi(epi_ctx *const *ctxs, int n_ctx, const epi_sweep_args *a) {
+  if (!ctxs || n_ctx < 1 || !a) return EPI_ERR_ARG;
+  for (int i = 0; i < n_ctx; ++i)
+    if (!ctxs[i]) return EPI_ERR_ARG;
+  if (n_ctx == 1) return epi_sweep(ctxs[0], a);
+  if (a->mem != EPI_MEM_HOST) {
+    ctxs[0]->err = "epi_sweep_multi: EPI_MEM_HOST only (device pointers belong to one GPU; shard on the caller's side "
+                   "and call epi_sweep per context instead)";
+    return EPI_ERR_ARG;
+  }
+  if (a->n_regions < 0 || a->n_eps < 1 || a->T < 1 || a->T_hist < 0 || a->T_hist > a->T || a->L < 1) {
+    ctxs[0]->err = "epi_sweep_multi: bad sizes";
+    return EPI_ERR_ARG;
+  }
+  const size_t nE = (size_t)a->n_eps, T = (size_t)a->T, L = (size_t)a->L, Th = (size_t)a->T_hist, Tf = T - Th;
+  const size_t B = (size_t)a->n_regions * nE;
+  std::vector<int> rc((size_t)n_ctx, EPI_OK);
+  std::vector<std::thread> th;
+  th.reserve((size_t)n_ctx);
+  for (int i = 0; i < n_ctx; ++i) {
+    const ShardPlan sp = shard_of(a->n_regions, n_ctx, i);
+    if (sp.hi <= sp.lo) continue;
+    th.emplace_back([=, &rc]() {
+      const size_t r0 = (size_t)sp.lo, nr = (size_t)(sp.hi - sp.lo), b0 = r0 * nE, nb = nr * nE;
+      epi_sweep_args s = *a;
+      s.n_regions = (int)nr;
+      auto adv = [](auto *p, size_t n) { return p ? p + n : p; };
+      s.prm = adv(a->prm, r0);
+      s.u = adv(a->u, r0 * T * L);
+      s.x = adv(a->x, r0 * T);
+      s.R = adv(a->R, r0 * T);
+      s.s_init = adv(a->s_init, r0 * 6); s.s_final = adv(a->s_final, r0 * 6);
+      s.Ps_init = adv(a->Ps_init, r0 * 36); s.Ps_final = adv(a->Ps_final, r0 * 36); s.Q = adv(a->Q, r0 * 36);
+      s.x0 = adv(a->x0, r0 * 3);
+      s.newcases_hist = adv(a->newcases_hist, r0 * Th);
+      s.weights = adv(a->weights, r0 * T * L);
+      s.noise_std = adv(a->noise_std, r0 * 3);
+      s.J0 = adv(a->J0, b0); s.J1 = adv(a->J1, b0);
+      s.on_front = adv(a->on_front, b0);
+      s.I_opt = adv(a->I_opt, r0);
+      s.u_knee = adv(a->u_knee, r0 * Tf * L);
+      // trajectory-minor arrays: rows of B values, this shard owns columns [b0, b0 + nb)
+      std::vector<double> noise, u_fore, P_first;
+      auto cut = [&](const double *src, size_t rows, std::vector<double> &dst) {
+        dst.resize(rows * nb);
+        for (size_t r = 0; r < rows; ++r) memcpy(dst.data() + r * nb, src + r * B + b0, nb * sizeof(double));
+      };
+      auto paste = [&](const std::vector<double> &src, size_t rows, double *dst) {
+        for (size_t r = 0; r < rows; ++r) memcpy(dst + r * B + b0, src.data() + r * nb, nb * sizeof(double));
+      };
+      if (a->noise) { cut(a->noise, Tf * 3, noise); s.noise = noise.data(); }
+      if (a->u_fore) { u_fore.resize(Tf * L * nb); s.u_fore = u_fore.data(); }
+      if (a->P_first) { P_first.resize(36 * nb); s.P_first = P_first.data(); }
+      rc[(size_t)i] = epi_sweep(ctxs[i], &s);
+      if (rc[(size_t)i] == EPI_OK) {
+        if (a->u_fore) paste(u_fore, Tf * L, a->u_fore);
+        if (a->P_first) paste(P_first, 36, a->P_first);
+      }
+    });
+  }
+  for (auto &t : th) t.join();
+  for (int i = 0; i < n_ctx; ++i)
+    if (rc[(size_t)i] != EPI_OK) {
+      if (i != 0) ctxs[0]->err = "shard " + std::to_string(i) + ": " + ctxs[i]->err;
+      return rc[(size_t)i];
+    }
+  return EPI_OK;
 }

@@ -471,11 +471,13 @@ class Engine:
     def sweep(self, prm, eps, u, x, R, s_init, Ps_init, s_final, Ps_final, Q, x0, newcases_hist,
               weights, *, n_regions, T, T_hist, L, beta_ekf=1.0, gamma_ekf=0.995, W=21,
               noise_std=None, noise=None, want_front=True, want_u_knee=False, want_u_fore=False,
-              want_P_first=False, out=None, lean=False):
+              want_P_first=False, out=None, lean=False, peers=None):
         """The optimal-NPI Pareto sweep (TrainPredictPrescribeNPI.m:421-495,624-633) for all
         regions x all epsilon.  Per-region arrays are [n_regions, ...] row-major with the
         MATLAB column-major page inside ([T,L] days-major, [36] column-major).  `out`
-        may carry preallocated J0/J1/on_front/I_opt buffers (device mode) for reuse."""
+        may carry preallocated J0/J1/on_front/I_opt buffers (device mode) for reuse.
+        `peers`: Engines on OTHER GPUs -- the one blocking call then shards the regions over
+        [self] + peers (epi_sweep_multi; host arrays only) and returns the same arrays, bit for bit."""
         mem = self._mode(eps, u, x, R, s_init, Ps_init, s_final, Ps_final, Q, x0, newcases_hist,
                          weights, noise)
         nR, nE = int(n_regions), int(eps.shape[0])
@@ -527,7 +529,13 @@ class Engine:
         if want_P_first:
             a.P_first = outbuf("P_first", (36, B))
         try:
-            self._ck(self._lib.epi_sweep(self._h, C.byref(a)))
+            if peers:
+                if mem != K.MEM_HOST:
+                    raise ValueError("sweep(peers=...): host arrays only (device arrays belong to one GPU)")
+                hs = (C.c_void_p * (1 + len(peers)))(self._h, *[p._h for p in peers])
+                self._ck(self._lib.epi_sweep_multi(hs, 1 + len(peers), C.byref(a)))
+            else:
+                self._ck(self._lib.epi_sweep(self._h, C.byref(a)))
         finally:
             self._done()
         return res

@@ -341,6 +341,18 @@ typedef struct {
 } epi_sweep_args;
 int epi_sweep(epi_ctx *ctx, const epi_sweep_args *a);
 
+/* The same sweep on several GPUs from ONE blocking host call ----------------------
+ * replaces the region loop of Tools/TrainPredictPrescribeNPI.m:93 around the call site :460 for a host
+ * (MATLAB/Octave through matlab/epi_mex.cpp, or any single process) that owns every GPU of the box:
+ * ctxs[i] is a context created on GPU i (epi_create(i, ...)); regions are sharded in contiguous blocks of
+ * ceil(n_regions / n_ctx), shard i runs as one epi_sweep on ctxs[i] from its own host thread, and every
+ * output lands in the caller's arrays exactly where the single-GPU call puts it (J0/J1/on_front [n_regions]
+ * [n_eps], I_opt [n_regions], u_knee, u_fore, P_first) -- bit-identical to epi_sweep on one context.
+ * a->mem must be EPI_MEM_HOST (device pointers belong to one GPU).  No collective is involved: the gather is
+ * each shard's device-to-host copy.  On error the code of the first failing shard is returned and
+ * epi_last_error(ctxs[0]) names it.  n_ctx == 1 is epi_sweep. */
+int epi_sweep_multi(epi_ctx *const *ctxs, int n_ctx, const epi_sweep_args *a);
+
 #ifdef __cplusplus
 }
 #endif

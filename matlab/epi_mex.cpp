@@ -23,7 +23,11 @@
 
 static epi_ctx *g_ctx = nullptr;
 
+// contexts on the other GPUs of the box (g_ctx is GPU 0): created on first use by the multi-GPU sweep
+static std::vector<epi_ctx *> g_peers;
 static void at_exit() {
+  for (epi_ctx *p : g_peers) epi_destroy(p);
+  g_peers.clear();
   if (g_ctx) { epi_destroy(g_ctx); g_ctx = nullptr; }
 }
 static epi_ctx *ctx() {
@@ -33,6 +37,22 @@ static epi_ctx *ctx() {
     mexAtExit(at_exit);
   }
   return g_ctx;
+}
+// [ctx 0, ctx 1, ...] for up to n_gpus GPUs (n_gpus <= 0: every GPU epi_create accepts)
+static std::vector<epi_ctx *> ctxs(int n_gpus) {
+  std::vector<epi_ctx *> v(1, ctx());
+  for (int d = 1; n_gpus <= 0 || d < n_gpus; ++d) {
+    if ((size_t)d > g_peers.size()) {
+      epi_ctx *c = nullptr;
+      if (epi_create(d, &c) != EPI_OK) {
+        if (n_gpus > 0) mexErrMsgIdAndTxt("epi:create", "GPU %d: %s", d, epi_last_error(nullptr));
+        break;  // no more devices
+      }
+      g_peers.push_back(c);
+    }
+    v.push_back(g_peers[(size_t)d - 1]);
+  }
+  return v;
 }
 static void check(int rc) {
   if (rc == EPI_OK) return;
@@ -203,21 +223,29 @@ static void cmd_pareto(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[
 //   epi_mex('ekf_eks', model, u, x, params, s_init, Ps_init, s_final, Ps_final, w_bar, v_bar, Q_w, R_v,
 //           beta, gamma, inv_monitor_len, order)
 // Q/R shape dispatch follows GenericExtendedKalmanFilter.m:64-91.
-static void cmd_ekf(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+// arguments 0..15 of 'ekf_eks' -> epi_ekf_args (one trajectory; Q/R shape dispatch of :64-91)
+struct EkfCall {
+  epi_ekf_args a;
+  epi_model_params p;
+  std::vector<double> qbuf;
+  int m, L, T;
+  bool legacy;
+};
+static void ekf_fill(EkfCall &c, int nrhs, const mxArray *prhs[]) {
   if (nrhs < 16) mexErrMsgIdAndTxt("epi:arg", "ekf_eks: 16 arguments expected");
+  epi_ekf_args &a = c.a;
+  std::vector<double> &qbuf = c.qbuf;
   const int model = (int)scalar(prhs[0]);
   const int m = model >= EPI_MODEL_OPTCTRL ? 6 : 3;
   const int L = (int)mxGetM(prhs[1]), T = (int)mxGetN(prhs[1]);
   if ((int)mxGetNumberOfElements(prhs[2]) != T) mexErrMsgIdAndTxt("epi:arg", "x must be 1 x T");
-  epi_model_params p = to_params(prhs[3], L);
-  epi_ekf_args a;
+  c.p = to_params(prhs[3], L);
   std::memset(&a, 0, sizeof a);
-  a.mem = EPI_MEM_HOST; a.model = model; a.B = 1; a.T = T; a.L = L; a.G = 1; a.prm = &p;
+  a.mem = EPI_MEM_HOST; a.model = model; a.B = 1; a.T = T; a.L = L; a.G = 1; a.prm = &c.p;
   a.u = dbl(prhs[1]); a.x = dbl(prhs[2]);
   a.s_init = dbl(prhs[4]); a.Ps_init = dbl(prhs[5]); a.s_final = dbl(prhs[6]); a.Ps_final = dbl(prhs[7]);
   a.v_bar = scalar(prhs[9]);
   // Q_w
-  std::vector<double> qbuf;
   const mxArray *Q = prhs[10];
   const size_t qr = mxGetM(Q), qn = mxGetNumberOfElements(Q);
   const size_t qc = mxGetNumberOfDimensions(Q) > 2 ? mxGetDimensions(Q)[1] : mxGetN(Q);
@@ -242,6 +270,15 @@ static void cmd_ekf(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) 
   else mexErrMsgIdAndTxt("epi:covShape", "Observation noise covariance noise mismatch");
   a.R = dbl(R);
   a.beta = scalar(prhs[12]); a.gamma = scalar(prhs[13]); a.W = (int)scalar(prhs[14]); a.order = (int)scalar(prhs[15]);
+  c.m = m; c.L = L; c.T = T; c.legacy = legacy;
+}
+
+static void cmd_ekf(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+  EkfCall c;
+  ekf_fill(c, nrhs, prhs);
+  epi_ekf_args &a = c.a;
+  const int m = c.m, L = c.L, T = c.T;
+  const bool legacy = c.legacy;
   const mwSize d3[3] = {(mwSize)m, (mwSize)m, (mwSize)T}, dk[3] = {(mwSize)m, 1, (mwSize)T};
   mxArray *o[11];
   o[0] = mxCreateDoubleMatrix(L, T, mxREAL); o[1] = mxCreateDoubleMatrix(L, T, mxREAL);
@@ -261,9 +298,44 @@ static void cmd_ekf(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) 
   }
 }
 
+// [S_PLUS, S_SMOOTH] = epi_mex('ekf_eks_masked', model, u, x, params, s_init, Ps_init, s_final, Ps_final, w_bar,
+//                              v_bar, Q_w, R_v, beta, gamma, inv_monitor_len, order, num_forecast_days)
+// The masked-horizon re-runs of Tools/ForecastQualityAssessment.m:383-386 as ONE batch: trajectory `start`
+// (1..num_forecast_days) is the same call with observations(T-start+1 : T) = NaN.  S_PLUS, S_SMOOTH come back
+// as m x T x num_forecast_days (page `start` = what the reference's loop iteration computes).
+static void cmd_ekf_masked(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+  if (nrhs < 17) mexErrMsgIdAndTxt("epi:arg", "ekf_eks_masked: 17 arguments expected");
+  EkfCall c;
+  ekf_fill(c, nrhs, prhs);
+  epi_ekf_args &a = c.a;
+  const int m = c.m, T = c.T, nf = (int)scalar(prhs[16]);
+  if (nf < 1 || nf > T) mexErrMsgIdAndTxt("epi:arg", "ekf_eks_masked: num_forecast_days must be in 1..T");
+  const double *x = dbl(prhs[2]);
+  std::vector<double> xb((size_t)T * nf);            // [T][B], B = nf
+  for (int t = 0; t < T; ++t)
+    for (int b = 0; b < nf; ++b) xb[(size_t)t * nf + b] = (t >= T - (b + 1)) ? mxGetNaN() : x[t];
+  a.B = nf; a.G = nf; a.x_per_traj = 1; a.x = xb.data();
+  std::vector<double> sp((size_t)T * m * nf), ss((size_t)T * m * nf);   // ABI layout [T][m][B]
+  a.S_PLUS = sp.data(); a.S_SMOOTH = ss.data();
+  check(epi_ekf_eks_batch(ctx(), &a));
+  const mwSize d3[3] = {(mwSize)m, (mwSize)T, (mwSize)nf};
+  mxArray *o[2] = {mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL), mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL)};
+  const std::vector<double> *src[2] = {&sp, &ss};
+  for (int k = 0; k < 2; ++k) {
+    double *dst = mxGetPr(o[k]);
+    for (int b = 0; b < nf; ++b)
+      for (int t = 0; t < T; ++t)
+        for (int i = 0; i < m; ++i) dst[(size_t)i + (size_t)m * ((size_t)t + (size_t)T * b)] = (*src[k])[((size_t)t * m + i) * nf + b];
+  }
+  plhs[0] = o[0];
+  if (nlhs > 1) plhs[1] = o[1]; else mxDestroyArray(o[1]);
+}
+
 // [J0, J1, on_front, I_opt, u_knee] = epi_mex('sweep', params(1xnR struct array), eps(1xnE), u(LxTxnR),
 //     x(TxnR), R(TxnR), s_init(6xnR), Ps_init(6x6xnR), s_final(6xnR), Ps_final(6x6xnR), Q(6x6xnR),
-//     beta_ekf, gamma_ekf, W, x0(3xnR), newcases_hist(T_histxnR), weights(LxTxnR), lean)
+//     beta_ekf, gamma_ekf, W, x0(3xnR), newcases_hist(T_histxnR), weights(LxTxnR), lean [, n_gpus])
+// n_gpus (optional, default 1): shard the regions over that many GPUs of the box in this one blocking call
+// (epi_sweep_multi; 0 = all GPUs); the outputs are the same arrays, bit for bit.
 // The batched form of the loop body of Tools/TrainPredictPrescribeNPI.m:421-495 + :624-633 for all
 // regions x all epsilon.  MATLAB's column-major (L x T x nR) is the ABI's per-region [T][L] layout.
 // Outputs: J0, J1, on_front are nE x nR; I_opt 1 x nR (1-based); u_knee L x T_fore x nR.
@@ -305,7 +377,13 @@ static void cmd_sweep(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]
   mxArray *oK = mxCreateNumericArray(3, kd, mxDOUBLE_CLASS, mxREAL);
   a.J0 = mxGetPr(oJ0); a.J1 = mxGetPr(oJ1); a.on_front = (unsigned char *)mxGetLogicals(oF);
   a.I_opt = iopt.data(); a.u_knee = mxGetPr(oK);
-  check(epi_sweep(ctx(), &a));
+  const int n_gpus = nrhs > 17 ? (int)scalar(prhs[17]) : 1;
+  if (n_gpus == 1) {
+    check(epi_sweep(ctx(), &a));
+  } else {
+    std::vector<epi_ctx *> cs = ctxs(n_gpus);
+    check(epi_sweep_multi(cs.data(), (int)cs.size(), &a));
+  }
   mxArray *oI = mxCreateDoubleMatrix(1, nR, mxREAL);
   for (int r = 0; r < nR; ++r) mxGetPr(oI)[r] = (double)(iopt[(size_t)r] + 1);
   mxArray *o[5] = {oJ0, oJ1, oF, oI, oK};
@@ -327,6 +405,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
   else if (c == "rt_expfit") cmd_rt_expfit(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "pareto") cmd_pareto(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "ekf_eks") cmd_ekf(nlhs, plhs, nrhs - 1, prhs + 1);
+  else if (c == "ekf_eks_masked") cmd_ekf_masked(nlhs, plhs, nrhs - 1, prhs + 1);
   else if (c == "sweep") cmd_sweep(nlhs, plhs, nrhs - 1, prhs + 1);
   else mexErrMsgIdAndTxt("epi:arg", "unknown command '%s'", cmd);
 }

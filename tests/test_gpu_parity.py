@@ -1005,3 +1005,37 @@ def test_config5_monte_carlo_scoring_wide(engine):
                                         reg["a"][r], reg["b"][r], syn.BETA, 0.0, 0.0, 0.0, Kn, 1.0)
         j0, j1 = o.NPICost((s * i) * al, uh[:, :, bb].T.astype(float), w[r].T)
         assert float(res["J0"][bb]) == j0 and float(res["J1"][bb]) == j1, bb
+
+
+# ------------------------------------------------------------------------------ multi-GPU through the C ABI
+@pytest.mark.parametrize("n_regions", [5, 2, 1])
+def test_sweep_multi_gpu_one_host_call(engine, n_regions):
+    """epi_sweep_multi: ONE blocking host-memory call shards the regions over the GPUs of the box
+    (TrainPredictPrescribeNPI.m:93 is the region loop) and returns the same arrays as the single-GPU call,
+    bit for bit -- including the trajectory-minor ones (noise in; u_fore, P_first out) that go through
+    per-shard staging, ragged shards and shards with no region at all."""
+    import torch
+    from epidemicmodeling_b200.api import get_engine
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    peers = [get_engine(d) for d in range(1, min(n_dev, 4))]
+    inp, eps = cases.sweep_case(n_regions=n_regions, n_eps=7, T_hist=35, T_fore=14)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    B, Tf = n_regions * eps.size, 14
+    rng = np.random.default_rng(5)
+    noise = rng.standard_normal((Tf, 3, B))
+    nstd = np.array([r["setup3"]["noise_std"] for r in inp])
+    kw = dict(noise=noise, noise_std=nstd, want_front=True, want_u_knee=True, want_u_fore=True, want_P_first=True)
+    one = wl.run_sweep(engine, batch, eps, **kw)
+    multi = wl.run_sweep(engine, batch, eps, peers=peers, **kw)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_knee", "u_fore", "P_first"):
+        assert_bits(multi[k], one[k], f"multi-GPU {k} (n_regions={n_regions}, {1 + len(peers)} GPUs)")
+    # the peers really worked: their contexts launched kernels (unless they had no region to take)
+    if n_regions >= 2:
+        assert peers[0].launch_count > 0
+    # device arrays belong to one GPU: refused, not silently run on one device
+    dbatch = wl.sweep_to_device(batch, eps, "cuda:0")
+    with pytest.raises(ValueError):
+        wl.run_sweep(engine, dbatch, eps, peers=peers)
