@@ -542,6 +542,45 @@ def main():
         torch.cuda.empty_cache()
         eng.release_cache()
 
+    # N > 1 extra: the whole 236-region sweep through ONE blocking host-memory call on all N GPUs
+    # (epi_sweep_multi: what a single-process MATLAB/Octave host gets).  Rank 0 drives every GPU; the other
+    # ranks wait on a CPU (gloo) barrier so that their devices are idle.
+    host_multi = None
+    if world > 1 and not a.no_e2e:
+        drain()
+        torch.cuda.synchronize()
+        cpu_group = dist.new_group(backend="gloo")
+        dist.barrier(group=cpu_group)
+        if rank == 0:
+            try:
+                peers = [Engine(d) for d in range(world) if d != local]
+                S_all = wl.run_fixed_input(eng, inp_all)
+                full_batch = wl.sweep_batch(inp_all, S_all)
+                hb = dict(full_batch)
+                for k in wl._SWEEP_ARRAYS:
+                    hb[k] = torch.from_numpy(np.array(full_batch[k], dtype=np.float64, order="C", copy=True)).pin_memory().numpy()
+                heps = np.array(eps, dtype=np.float64, copy=True)
+                hout = {"J0": np.empty((nR, nE)), "J1": np.empty((nR, nE)), "on_front": np.empty((nR, nE), dtype=np.uint8),
+                        "I_opt": np.empty((nR,), dtype=np.int32)}
+                call = lambda: wl.run_sweep(eng, hb, heps, out=hout, peers=peers)
+                for _ in range(3):
+                    call()
+                walls = []
+                for _ in range(a.steps):
+                    tw0 = time.perf_counter()
+                    call()
+                    walls.append((time.perf_counter() - tw0) * 1e3)
+                ms_hm = float(np.mean(walls))
+                host_multi = {"value": units_total / (ms_hm * 1e-3), "unit": "trajectory-days/s", "ms_per_call": ms_hm,
+                              "ms_per_call_min": float(min(walls)), "ms_per_call_max": float(max(walls)), "gpus": world,
+                              "timing": "host wall clock around the blocking call (H2D, kernels, D2H on every GPU inside)",
+                              "note": "one process, one call: include/epi_b200.h epi_sweep_multi; pinned host buffers"}
+                for p_ in peers:
+                    p_.close()
+            except Exception as exc:
+                host_multi = {"error": repr(exc)}
+        dist.barrier(group=cpu_group)
+
     # ---- roofline of the dominant kernel
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -639,7 +678,7 @@ def main():
                            "mode_value": "EPI_MEM_DEVICE (inputs resident in HBM)",
                            "mode_e2e": "EPI_MEM_HOST (host buffers, blocking call; pinned = headline, pageable beside it)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "strong_scaling": strong, "replica_weak": replica, "secondary": secondary,
+                "cpu_baseline": cpu, "strong_scaling": strong, "host_multi_call": host_multi, "replica_weak": replica, "secondary": secondary,
                 "lean_mode": None if ms_lean is None else {
                               "value": units_total / (ms_lean * 1e-3), "unit": "trajectory-days/s",
                               "ms_per_step": ms_lean, "outputs_bit_identical_to_full": lean_same,

@@ -44,6 +44,8 @@ mxLogical *mxGetLogicals(const mxArray *);
 void mxDestroyArray(mxArray *);
 void mexErrMsgIdAndTxt(const char *, const char *, ...);
 int mexAtExit(void (*)(void));
+/* the gateway entry point has C linkage in the real mex.h too */
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]);
 #ifdef __cplusplus
 }
 #endif
