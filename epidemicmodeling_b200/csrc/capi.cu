@@ -57,6 +57,11 @@ struct epi_ctx {
   // weights: 12.7 MB that upload beside the forward pass instead of in front of it)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[2] = {nullptr, nullptr};
+  // EPI_MEM_DEVICE calls cannot read their epi_model_params on the host without draining the stream: a
+  // one-CTA kernel checks them on the device and records the first violation in this mapped host word
+  // (EPI_ERR_* code); it is reported by the next epi_sync or the next call on the context.
+  int *deferred_err = nullptr;      // pinned, device-mapped
+  int *deferred_err_dev = nullptr;
 };
 
 namespace {
@@ -73,6 +78,7 @@ namespace {
   } while (0)
 
 [[noreturn]] void bad_arg(const std::string &m, int code = EPI_ERR_ARG) { throw EpiError{code, m}; }
+constexpr int kMaxDynSmem = 232448;  // 227 KB: the opt-in dynamic shared memory limit of one CTA on sm_100
 
 cudaEvent_t get_event(epi_ctx *c) {
   if (!c->ev_pool.empty()) {
@@ -253,6 +259,16 @@ long long plan_wave(epi_ctx *c, long long B, size_t per) {
   return w;
 }
 
+void take_deferred_error(epi_ctx *c) {
+  if (!c->deferred_err) return;
+  const int code = *(volatile int *)c->deferred_err;
+  if (!code) return;
+  *c->deferred_err = 0;
+  throw EpiError{code, code == EPI_ERR_OBS_TYPE
+                           ? "unknown observation type (found on the device in an earlier EPI_MEM_DEVICE call)"  // SIAlphaModelEKF.m:57
+                           : "epi_model_params.L does not match args.L (found on the device in an earlier EPI_MEM_DEVICE call)"};
+}
+
 template <class F>
 int guarded(epi_ctx *ctx, F &&f) {
   if (!ctx) return EPI_ERR_ARG;
@@ -270,6 +286,7 @@ int guarded(epi_ctx *ctx, F &&f) {
   };
   try {
     DeviceScope scope(ctx->device);
+    take_deferred_error(ctx);   // a violation a previous EPI_MEM_DEVICE call found on the device
     f();
     ctx->err.clear();
     return EPI_OK;
@@ -364,6 +381,7 @@ extern "C" void epi_destroy(epi_ctx *c) {
     cudaEventDestroy(c->copy_ev[1]);
   }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->deferred_err) cudaFreeHost(c->deferred_err);
   delete c;
 }
 
@@ -381,7 +399,10 @@ extern "C" int epi_set_stream(epi_ctx *c, void *s) {
 }
 
 extern "C" int epi_sync(epi_ctx *c) {
-  return guarded(c, [&] { CK(cudaStreamSynchronize(c->stream)); });
+  return guarded(c, [&] {
+    CK(cudaStreamSynchronize(c->stream));
+    take_deferred_error(c);
+  });
 }
 
 extern "C" int epi_set_scratch_limit(epi_ctx *c, size_t bytes) {
@@ -722,6 +743,9 @@ extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
     check_mem(a->mem);
     if (a->B < 0 || a->T < 0 || a->G < 1 || a->W < 1) bad_arg("epi_rt_expfit_batch: bad B/T/G/W");
     if (a->order != 1 && a->order != 2) bad_arg("Undefined order", EPI_ERR_ORDER);  // Rt_ExpFitEKF.m:47,75
+    if (a->W > kMaxDynSmem / (3 * 8 * 64))
+      bad_arg("inv_monitor_len = " + std::to_string(a->W) + " exceeds the window the device kernel holds in shared memory (max " +
+              std::to_string(kMaxDynSmem / (3 * 8 * 64)) + ")");
     if (a->B == 0 || a->T == 0) return;
     if (!a->x || !a->s_init || !a->params || !a->w_bar || !a->Ps_init || !a->Q || !a->R)
       bad_arg("epi_rt_expfit_batch: a required array is null");
@@ -773,6 +797,28 @@ extern "C" int epi_rt_expfit_batch(epi_ctx *c, const epi_rt_expfit_args *a) {
 // ---------------------------------------------------------------------------
 namespace {
 
+__global__ void validate_params_kernel(const epi_model_params *prm, long long n, int L, int model, int *flag) {
+  for (long long g = threadIdx.x; g < n; g += blockDim.x) {
+    int code = 0;
+    if (prm[g].L != L) code = EPI_ERR_ARG;
+    else if (model != EPI_MODEL_LEGACY_CODEGEN && prm[g].obs_type != EPI_OBS_NEWCASES && prm[g].obs_type != EPI_OBS_TOTALCASES)
+      code = EPI_ERR_OBS_TYPE;
+    if (code) atomicCAS(flag, 0, code);
+  }
+}
+
+// the device-memory form of validate_params_host below: no host read, no stream drain
+void validate_params_device(epi_ctx *c, const epi_model_params *prm, long long n, int L, int model) {
+  if (n <= 0) return;
+  if (!c->deferred_err) {
+    CK(cudaHostAlloc((void **)&c->deferred_err, sizeof(int), cudaHostAllocMapped));
+    *c->deferred_err = 0;
+    CK(cudaHostGetDevicePointer((void **)&c->deferred_err_dev, c->deferred_err, 0));
+  }
+  validate_params_kernel<<<1, 128, 0, c->stream>>>(prm, n, L, model, c->deferred_err_dev);
+  check_launch(c, 1);
+}
+
 void validate_params_host(const epi_model_params *prm, long long n, int L, int model) {
   for (long long g = 0; g < n; ++g) {
     if (prm[g].L != L) bad_arg("epi_model_params.L does not match args.L");
@@ -796,6 +842,14 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
       bad_arg("Process noise covariance noise mismatch", EPI_ERR_QR_SHAPE);  // :75
     if (a->r_mode != EPI_R_CONST && a->r_mode != EPI_R_PERDAY)
       bad_arg("Observation noise covariance noise mismatch", EPI_ERR_QR_SHAPE);  // :90
+    // the innovation-monitor window (GenericExtendedKalmanFilter.m:170-181) is a shared-memory ring of
+    // 3 * W doubles per thread (csrc/ekf_forward.cu: 64-thread CTAs for m = 3, 32 for m = 6; 227 KB per CTA)
+    {
+      const int w_max = kMaxDynSmem / (3 * 8 * (model_dim(a->model) == 6 ? 32 : 64));
+      if (a->W > w_max)
+        bad_arg("inv_monitor_len = " + std::to_string(a->W) + " exceeds the window the device kernels hold in shared memory (max " +
+                std::to_string(w_max) + " for this model)");
+    }
     const bool legacy = model_legacy(a->model);
     if (legacy && (a->q_mode != EPI_Q_CONST || a->r_mode != EPI_R_CONST))
       bad_arg("the legacy estimator takes a constant Q and a scalar R", EPI_ERR_QR_SHAPE);
@@ -807,6 +861,7 @@ extern "C" int epi_ekf_eks_batch(epi_ctx *c, const epi_ekf_args *a) {
     const long long B = a->B;
     const long long n_groups = (B + a->G - 1) / a->G;
     if (a->mem == EPI_MEM_HOST) validate_params_host(a->prm, n_groups, L, a->model);
+    else validate_params_device(c, a->prm, n_groups, L, a->model);
 
     Call shared(c, a->mem);
     const epi_model_params *prm = shared.in(a->prm, (size_t)n_groups);
@@ -995,6 +1050,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     const long long nR = a->n_regions, B = nR * a->n_eps;
     const bool host = a->mem == EPI_MEM_HOST;
     if (host) validate_params_host(a->prm, nR, L, EPI_MODEL_OPTCTRL);
+    else validate_params_device(c, a->prm, nR, L, EPI_MODEL_OPTCTRL);
     tr.mark("validate");
 
     Call shared(c, a->mem);

@@ -1039,3 +1039,71 @@ def test_sweep_multi_gpu_one_host_call(engine, n_regions):
     dbatch = wl.sweep_to_device(batch, eps, "cuda:0")
     with pytest.raises(ValueError):
         wl.run_sweep(engine, dbatch, eps, peers=peers)
+
+
+# ------------------------------------------------------------------------------ round-2 robustness items
+def test_device_mode_validates_params_without_draining_the_stream(engine):
+    """EPI_MEM_DEVICE calls cannot read epi_model_params on the host: a one-CTA kernel checks them and the
+    violation ('unknown observation type', SIAlphaModelEKF.m:57) surfaces at the next sync / call."""
+    import torch
+    from epidemicmodeling_b200.engine import params_to_device
+    inp, b, x, nRep = _ekf3_replicate_batch(nR=2, nRep=8)
+    B, T, L = x.shape[1], b["T"], b["L"]
+    kw = dict(B=B, T=T, L=L, G=nRep, x_per_traj=True, r_mode=K.R_PERDAY, fixed_R=False, beta=b["beta"], gamma=b["gamma"],
+              W=b["W"], outputs=("S_SMOOTH",))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    args = [dev(b[k]) for k in ("u",)] + [dev(x), dev(b["R"]), dev(b["Q"]), dev(b["s_init"]), dev(b["Ps_init"]),
+                                          dev(b["s_final"]), dev(b["Ps_final"])]
+    bad = pack_params([dict(r["setup3"]["params"]) for r in inp], L)
+    bad[1].obs_type = 7
+    engine.ekf_eks(K.MODEL_SIALPHA, params_to_device(bad, "cuda:0"), *args, **kw)      # enqueued, no error yet
+    with pytest.raises(K.EpiError) as e:
+        engine.sync()
+    assert e.value.code == K.ERR_OBS_TYPE and "unknown observation type" in e.value.msg
+    engine.sync()                                                                       # reported once
+    good = engine.ekf_eks(K.MODEL_SIALPHA, params_to_device(b["prm"], "cuda:0"), *args, **kw)
+    engine.sync()
+    host = engine.ekf_eks(K.MODEL_SIALPHA, b["prm"], b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"], b["s_final"],
+                          b["Ps_final"], **kw)
+    assert_bits(good["S_SMOOTH"].cpu().numpy(), host["S_SMOOTH"], "device mode after a reported violation")
+    with pytest.raises(K.EpiError) as e:                                                # host mode: immediate
+        engine.ekf_eks(K.MODEL_SIALPHA, bad, b["u"], x, b["R"], b["Q"], b["s_init"], b["Ps_init"], b["s_final"],
+                       b["Ps_final"], **kw)
+    assert e.value.code == K.ERR_OBS_TYPE
+
+
+def test_monitor_window_limit_is_a_clear_argument_error(engine):
+    """The innovation-monitor window lives in shared memory: a window that cannot fit is refused with a message
+    that says so (the reference accepts any inv_monitor_len; 151 days for m = 3, 302 for m = 6)."""
+    c = cases.ekf3_case(0, T_hist=40, T_fore=10)
+    from epidemicmodeling_b200 import api
+    a = lambda W: api.SIAlphaModelEKF(c["u"], c["x"], c["params"], c["s_init"], c["Ps_init"], c["s_final"], c["Ps_final"],
+                                     c["w_bar"], c["v_bar"], c["Q_w"], c["R_v"], c["beta"], c["gamma"], W, 1)
+    ok = a(151)
+    o = orc()
+    want = o.ekf_eks(o.SIALPHA, *ekf_args(dict(c, inv_monitor_len=151)))
+    assert_bits(ok[4], want["S_SMOOTH"], "W = 151 S_SMOOTH"); assert_bits(ok[10], want["rho"], "W = 151 rho")
+    with pytest.raises(K.EpiError) as e:
+        a(152)
+    assert e.value.code == K.ERR_ARG and "inv_monitor_len" in e.value.msg and "shared memory" in e.value.msg
+
+
+def test_random_schedules_device_mode_on_a_fresh_engine():
+    """Engine.random_schedules(device=True) as the FIRST call of a context: the kernel must run on torch's
+    current stream (the output tensor and the temporary params tensor belong to it)."""
+    import torch
+    from epidemicmodeling_b200.engine import Engine
+    nR, nS, Kn, L = 2, 33, 21, 12
+    reg = syn.load_regions(nR)
+    prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                            u_min=np.zeros(L), alpha_min=1e-8, alpha_max=100.0) for r in range(nR)], L)
+    fresh = Engine(0)
+    try:
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            ud = fresh.random_schedules(prm, nR * nS, Kn, L, nS, 99, device=True)
+            got = ud.cpu().numpy()                     # ordered after the kernel on the same stream
+        uh = fresh.random_schedules(prm, nR * nS, Kn, L, nS, 99)
+        assert np.array_equal(got, uh)
+    finally:
+        fresh.close()
