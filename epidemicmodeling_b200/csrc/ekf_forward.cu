@@ -464,6 +464,10 @@ int forward_resident_slots6() {
 void launch_ekf_forward(const EkfParams &p, cudaStream_t st) {
   // the monitor is dead code unless rho is wanted or R adapts (beta != 1)
   const bool monitor = (p.rho.p != nullptr) || (p.beta != 1.0);
+  if (rows_forward_ok(p) && rows_wanted(p.B, true)) {   // small batch: six lanes per trajectory (csrc/ekf_rows.cu)
+    launch_ekf_forward_rows(p, st);
+    return;
+  }
   if (p.fwd_segments > 1 && p.fwd_sync && p.tiled && !monitor) {
     bool done = false;
 #define CALL(MDL) done = launch_fwd_segmented<MDL>(p, st)

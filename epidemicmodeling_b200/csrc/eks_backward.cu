@@ -233,6 +233,10 @@ static void launch_bwd_model(const EkfParams &p, cudaStream_t st, bool want_p) {
 
 void launch_eks_backward(const EkfParams &p, cudaStream_t st) {
   const bool want_p = (p.P_SMOOTH.p != nullptr) || (p.P_first.p != nullptr);
+  if (rows_backward_ok(p) && rows_wanted(p.B, false)) {   // small batch: six lanes per trajectory (csrc/ekf_rows.cu)
+    launch_eks_backward_rows(p, st);
+    return;
+  }
 #define CALL(MDL)                                               \
   if (p.tiled) launch_bwd_model<MDL, true>(p, st, want_p);      \
   else launch_bwd_model<MDL, false>(p, st, want_p)

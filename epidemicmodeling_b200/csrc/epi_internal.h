@@ -74,6 +74,12 @@ int forward_segments(long long tiles, int slots);  // segment count minimising t
 int forward_resident_slots6();                     // resident one-warp CTAs of the m = 6 forward kernel on this device
 void launch_eks_gain(const EkfParams &p, cudaStream_t st);
 void launch_eks_backward(const EkfParams &p, cudaStream_t st);
+// lane-group forms (csrc/ekf_rows.cu): six lanes per trajectory, for small batches of the sweep's call shape
+void launch_ekf_forward_rows(const EkfParams &p, cudaStream_t st);
+void launch_eks_backward_rows(const EkfParams &p, cudaStream_t st);
+bool rows_forward_ok(const EkfParams &p);
+bool rows_backward_ok(const EkfParams &p);
+bool rows_wanted(long long B, bool forward);
 
 struct SeirpParams {
   int B, K, rate_mode, saturated, out_mode;

@@ -1107,3 +1107,48 @@ def test_random_schedules_device_mode_on_a_fresh_engine():
         assert np.array_equal(got, uh)
     finally:
         fresh.close()
+
+
+@pytest.mark.parametrize("shape", [(3, 15, 33, 21), (2, 7, 1, 9), (1, 4, 12, 0)])
+def test_lane_group_kernels_are_bit_identical(engine, shape, monkeypatch):
+    """csrc/ekf_rows.cu: six lanes per trajectory (one covariance row per lane) for the forward pass and the
+    smoother recursion of the sweep -- the same bits as the one-thread kernels, full and lean, with ragged warps
+    (5 trajectories per warp), and against the oracle."""
+    nR, nE, Th, Tf = shape
+    inp, eps = cases.sweep_case(n_regions=nR, n_eps=nE, T_hist=Th, T_fore=Tf)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    kw = dict(want_front=True, want_u_fore=True, want_u_knee=True)
+    monkeypatch.setenv("EPI_ROWS", "0")
+    monkeypatch.setenv("EPI_FWD_SEGMENTS", "1")
+    one = wl.run_sweep(engine, batch, eps, **kw)
+    monkeypatch.setenv("EPI_ROWS", "1")
+    rows = wl.run_sweep(engine, batch, eps, **kw)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+        assert_bits(rows[k], one[k], f"lane-group {k} {shape}")
+    lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+        assert_bits(lean[k], one[k], f"lane-group lean {k} {shape}")
+    o = orc()
+    for r, rin in enumerate(inp):
+        s6 = rin["setup6"]
+        Sr = S[:, :, r].T
+        reg = o.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                            s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21,
+                            Sr[0, Th - 1], Sr[1, Th - 1], Sr[2, Th - 1], (Sr[0, :Th] * Sr[1, :Th]) * Sr[2, :Th], rin["weights"])
+        j0, j1, m, io, _ = o.sweep_region(reg, eps)
+        assert_bits(rows["J0"][r], j0, f"lane-group J0 vs oracle {shape}"); assert_bits(rows["J1"][r], j1, "J1 vs oracle")
+    # the generic batched entry takes the same kernels when its tape is scratch (S_SMOOTH only)
+    c = cases.ekf6_case(1, T_hist=30, T_fore=11)
+    ee = np.array([1e-9, 1e-3, 0.05, 0.3, 0.7, 0.999, 0.2])
+    T, L = c["u"].shape[1], 12
+    cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+    call = lambda: engine.ekf_eks(K.MODEL_OPTCTRL, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], c["R_v"],
+                                  cm(c["Q_w"]), c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]),
+                                  B=ee.size, T=T, L=L, G=ee.size, epsilon=ee, r_mode=K.R_PERDAY, fixed_R=False,
+                                  beta=1.0, gamma=0.995, W=21, outputs=("S_SMOOTH", "u_opt_smooth"))
+    g_rows = call()
+    monkeypatch.setenv("EPI_ROWS", "0")
+    g_one = call()
+    for k in ("S_SMOOTH", "u_opt_smooth"):
+        assert_bits(g_rows[k], g_one[k], f"lane-group generic entry {k}")
