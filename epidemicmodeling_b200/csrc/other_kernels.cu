@@ -347,11 +347,13 @@ EPI_DI double stage_value(const double *p) { return *p; }
 
 // LC: compile-time number of NPIs (12, the OxCGRT shape) or 0 = runtime P.L.
 // SIMPLE: the Monte-Carlo scoring shape -- costs only (no trajectory outputs), no noise array.
-template <int U_KIND, int SB, int TT, int LC, bool SIMPLE>
+// NST: stages of the shared-memory ring (a stage is re-filled as soon as the CTA has consumed it, so NST - 1
+// stages are in flight while one is being integrated)
+template <int U_KIND, int SB, int TT, int LC, bool SIMPLE, int NST>
 __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constant__ RolloutParams P) {
   using U = typename std::conditional<U_KIND == EPI_U_U8, unsigned char, double>::type;
-  extern __shared__ __align__(128) unsigned char stage_raw[];  // [2][TT][L][SB] of U
-  __shared__ unsigned long long bars[2];
+  extern __shared__ __align__(128) unsigned char stage_raw[];  // [NST][TT][L][SB] of U
+  __shared__ unsigned long long bars[NST];
   __shared__ double wtile[TT * EPI_LMAX];  // this stage's day-wise weights (CTA within one group)
   const int tid = threadIdx.x;
   const long long blk0 = (long long)blockIdx.x * SB;
@@ -365,23 +367,25 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   const size_t us = (size_t)P.u_stride;
   const int n_stages = (K + TT - 1) / TT;
 
-  if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < NST; ++q) mbar_init(&bars[q], 1);
+  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   auto issue = [&](int sidx) {  // executed by warp 0
     const int t0 = sidx * TT;
     const int nt = (K - t0 < TT) ? (K - t0) : TT;
     const int rows = nt * L;
-    unsigned long long *bar = &bars[sidx & 1];
-    U *dst = stage_u + (size_t)(sidx & 1) * stage_elems;
+    unsigned long long *bar = &bars[sidx % NST];
+    U *dst = stage_u + (size_t)(sidx % NST) * stage_elems;
     if (tid == 0) mbar_expect_tx(bar, (unsigned)((size_t)rows * nb * sizeof(U)));
     __syncwarp();
     for (int r = tid; r < rows; r += 32)
       bulk_load_row(dst + (size_t)r * SB, gu + ((size_t)t0 * L + r) * us, (unsigned)(nb * sizeof(U)), bar);
   };
   if (tid < 32) {
-    issue(0);
-    if (n_stages > 1) issue(1);
+    for (int q = 0; q < NST && q < n_stages; ++q) issue(q);
   }
 
   const long long g = active ? (P.b0 + b) / P.G : 0;
@@ -413,8 +417,8 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
       for (int q = tid; q < nt * L; q += SB) wtile[q] = __ldg(P.w + ((size_t)g_first * K + t0) * L + q);
       __syncthreads();
     }
-    mbar_wait(&bars[sidx & 1], (unsigned)((sidx >> 1) & 1));
-    const U *__restrict__ su = stage_u + (size_t)(sidx & 1) * stage_elems + tid;
+    mbar_wait(&bars[sidx % NST], (unsigned)((sidx / NST) & 1));
+    const U *__restrict__ su = stage_u + (size_t)(sidx % NST) * stage_elems + tid;
     // the input term and the day's weighted cost do not depend on the state: evaluate them for DQ
     // days at once (independent FMA chains = instruction-level parallelism), then run the DQ
     // strictly sequential state updates.  FULL = a whole TT-day tile (constant trip counts).
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
       else run_tile(std::false_type{});
     }
     __syncthreads();  // everyone is done reading this buffer
-    if (tid < 32 && sidx + 2 < n_stages) issue(sidx + 2);
+    if (tid < 32 && sidx + NST < n_stages) issue(sidx + NST);
   }
   if (want_cost && active) {
     P.J0.p[P.J0.off + b] = a0 / (double)P.T_total;                        // NPICost.m:6
@@ -496,19 +500,23 @@ static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
 #ifndef EPI_ROLL_TT  // days per stage (uint8 schedules)
 #define EPI_ROLL_TT 16
 #endif
+#ifndef EPI_ROLL_NST  // stages of the ring (uint8 schedules)
+#define EPI_ROLL_NST 2
+#endif
   constexpr int SB = (U_KIND == EPI_U_U8) ? EPI_ROLL_SB : 256;
   constexpr int TT = (U_KIND == EPI_U_U8) ? EPI_ROLL_TT : 2;
+  constexpr int NST = (U_KIND == EPI_U_U8) ? EPI_ROLL_NST : 2;
   const size_t esz = (U_KIND == EPI_U_U8) ? 1 : 8;
   // TMA bulk copies need 16-byte aligned, 16-byte multiple rows
   if (p.K < 1 || p.B < 8 * SB || (((size_t)p.B * esz) & 15) || (((size_t)p.u_stride * esz) & 15) ||
       (((size_t)p.u_off * esz) & 15) || ((size_t)p.u & 15))
     return false;
-  const size_t smem = (size_t)2 * TT * p.L * SB * esz;
+  const size_t smem = (size_t)NST * TT * p.L * SB * esz;
   const unsigned grid = (unsigned)((p.B + SB - 1) / SB);
   const bool simple = p.J0.p && p.w && !p.noise.p && !p.s.p && !p.i.p && !p.alpha.p;
 #define EPI_LAUNCH_STAGED(LC, SIMPLE)                                                              \
   do {                                                                                             \
-    auto kern = rollout_staged_kernel<U_KIND, SB, TT, LC, SIMPLE>;                                 \
+    auto kern = rollout_staged_kernel<U_KIND, SB, TT, LC, SIMPLE, NST>;                                 \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     kern<<<grid, SB, smem, st>>>(p);                                                               \
   } while (0)
