@@ -117,7 +117,32 @@ def full(tag):
         print("wrote", path)
 
 
+def traffic(tag):
+    """profiles/<tag>_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch of every captured kernel
+    (bench.py reads roofline.traffic from it)."""
+    import json
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    out = {}
+    for rep in sorted(glob.glob(os.path.join(GO, "prof_*.ncu-rep"))):
+        kname = os.path.basename(rep)[5:-8]
+        rows = list(csv.reader(io.StringIO(ncu("-i", rep, "--page", "raw", "--csv"))))
+        if len(rows) < 3:
+            continue
+        col = {h: i for i, h in enumerate(rows[0])}
+        try:
+            rd = float(rows[2][col["dram__bytes_read.sum"]]) * scale[rows[1][col["dram__bytes_read.sum"]]]
+            wr = float(rows[2][col["dram__bytes_write.sum"]]) * scale[rows[1][col["dram__bytes_write.sum"]]]
+        except (KeyError, ValueError):
+            continue
+        out[kname] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "traffic": rd + wr}
+    out["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full (profiles/%s_*.md); forward/gain/backward "
+                    "on the bench workload 236x250x561; seirp_staged at B=500000, rollout_staged at B=5.9M" % tag)
+    json.dump(out, open(os.path.join(PR, f"{tag}_traffic.json"), "w"), indent=1)
+    print("wrote", os.path.join(PR, f"{tag}_traffic.json"))
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     launch_shares(tag)
     full(tag)
+    traffic(tag)
