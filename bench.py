@@ -452,6 +452,26 @@ def main():
             run_lean()
         ms_lean = timed_steps(run_lean, a.steps, fence) / a.steps
         lean_same = all(bool(torch.equal(out_lean[k], out1[k])) for k in out1)
+    elif not a.no_lean:
+        # N > 1: the same pipelined step (shard sweep + gather + Pareto tail) with the lean smoother
+        drain()
+        ref_J0 = full[(step_no[0] - 1) % nbuf]["J0"][:nR].clone()
+        ref_front = full[(step_no[0] - 1) % nbuf]["on_front"].clone()
+
+        def step_lean():
+            i = step_no[0] % nbuf
+            step_no[0] += 1
+            if comm_ev[i] is not None:
+                torch.cuda.current_stream().wait_event(comm_ev[i])
+            wl.run_sweep(eng, dbatch, None, out={"J0": loc[i]["J0"][:n_loc], "J1": loc[i]["J1"][:n_loc]}, want_front=False,
+                         lean=True)
+            tail_async(i)
+        for _ in range(3):
+            step_lean()
+        drain()
+        ms_lean = max_over_ranks(timed_steps(step_lean, a.steps, fence, drain)) / a.steps
+        last = (step_no[0] - 1) % nbuf
+        lean_same = bool(torch.equal(full[last]["J0"][:nR], ref_J0) and torch.equal(full[last]["on_front"], ref_front))
 
     # ---- e2e: the blocking host-memory C-ABI call (H2D + kernels + D2H inside the call), pinned and pageable buffers
     def e2e_leg(pin):

@@ -426,12 +426,13 @@ bool rows_backward_ok(const EkfParams &p) {
 }
 // 0 = never, 1 = always (when the shape allows), otherwise by batch size: the lane-group form pays once the
 // one-thread kernels cannot fill the machine (measured crossover)
-// EPI_ROWS=1 / 0 forces the lane-group kernels on (where the shape allows) / off; otherwise by batch size, from
-// the measurements in DESIGN.md 4 (B200, 561 days): the smoother recursion wins below ~8k trajectories (0.72 vs
-// 0.93 ms at 7500), the forward pass does not win at any size yet (1.76 vs 1.11 ms at 7500) and stays opt-in.
+// The lane-group kernels are opt-in (EPI_ROWS=1, where the call shape allows): with the measurements in DESIGN.md 4
+// neither form beats the tuned one-thread kernels (forward 1.27 vs 1.11 ms, recursion 0.72 vs 0.58 ms at 7500
+// trajectories x 561 days; further behind at larger batches).
 bool rows_wanted(long long B, bool forward) {
+  (void)B; (void)forward;
   if (const char *e = getenv("EPI_ROWS")) return atoi(e) != 0;   // read per call: tests and tuning runs toggle it
-  return !forward && B <= kRowsMaxBatch;
+  return false;
 }
 
 }  // namespace epi

@@ -17,8 +17,14 @@ struct BwdDay {
   double sp[M];  // S_PLUS(:, k)
 };
 
-template <int MODEL, bool WANT_P, bool TILED>
-__global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const __grid_constant__ EkfParams P) {
+// ROOMY (the sweep's call shape, chosen by the host through P.bwd_prefetch > 0): a 255-register budget instead of 128.
+// With 128 registers the kernel spills 200 bytes, and the spill STORE of a prefetched J entry has to wait for that
+// load -- the one-day-ahead register prefetch is exposed again (ncu, 7500 trajectories: 20 % of the stall samples on
+// two STL instructions).  Without spills, with the tape page three days ahead pulled into L2 and the per-group
+// scalars fetched a day ahead: 0.57 / 0.63 / 1.07 / 2.15 ms at 7.5k / 14.7k / 29.5k / 59k trajectories x 561 days
+// against 1.02 / 1.09 / 1.38 / 2.31 ms.  (Round 1 measured a register cap of 152 ALONE as a loss: 2.44 ms.)
+template <int MODEL, bool WANT_P, bool TILED, bool ROOMY = false>
+__global__ void __launch_bounds__(64, (WANT_P || ROOMY) ? 4 : 8) eks_backward_kernel(const __grid_constant__ EkfParams P) {
   constexpr int M = model_dim(MODEL);
   constexpr bool LEG = model_legacy(MODEL);
   constexpr bool SYM = !LEG;
@@ -42,7 +48,11 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
   const Tape<true> tDot = make_tape<true>(P.dot_day, 1, T, b), tCost = make_tape<true>(P.cost_day, 1, T, b);
 
   // writes the schedule of day `pos` implied by state `s5` (and the per-day scalars of the sweep)
-  auto emit_inputs = [&](int pos, const double *u_day, size_t u_js, double s5, bool use_group) {
+  const double nan = __longlong_as_double(0x7ff8000000000000ll);
+  // the per-group values of a day (NaN = evaluate per trajectory); the day loop fetches them one day ahead
+  auto group_pre = [&](int pos) { return in.dot_grp ? __ldg(in.dot_grp + pos) : nan; };
+  auto group_cost = [&](int pos) { return (want_cost && in.cost_grp) ? __ldg(in.cost_grp + pos) : (want_cost ? nan : 0.0); };
+  auto emit_inputs = [&](int pos, const double *u_day, size_t u_js, double s5, double pre, double prec) {
     double *uo = nullptr;
     size_t uo_s = 0;
     if (P.u_opt_smooth.p) {
@@ -53,9 +63,6 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
       uo_s = (size_t)P.u_fore.stride;
     }
     if (!uo && !P.dot_day.p) return;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    const double pre = (use_group && in.dot_grp) ? __ldg(in.dot_grp + pos) : nan;
-    const double prec = (use_group && want_cost && in.cost_grp) ? __ldg(in.cost_grp + pos) : (want_cost ? nan : 0.0);
     double dotv, costv;
     if (pre == pre && prec == prec) {
       dotv = pre;
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
     store_mat<M, false>(Ps, P.P_SMOOTH.p + (size_t)P.P_SMOOTH.off + b + (size_t)posT * MM * P.P_SMOOTH.stride,
                         (size_t)P.P_SMOOTH.stride);
   // u_opt_smooth(:, T) is never written by the reference => zeros (:95,:204)
-  if (!LEG) emit_inputs(posT, kZeroInputs, 1, 0.0, false);
+  if (!LEG) emit_inputs(posT, kZeroInputs, 1, 0.0, nan, want_cost ? nan : 0.0);
 
   auto load_day = [&](int k, BwdDay<M> &d) {
     const int pos = REV ? (T - 1 - k) : k;
@@ -148,12 +155,35 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
     for (int i = 0; i < M; ++i) { d.sm[i] = a[tSm.f(i)]; d.sp[i] = c[tSp.f(i)]; }
   };
 
+  // the recursion is bound by the latency of the next day's tape page (one thread walks T days): pull the page of
+  // day k - P.bwd_prefetch into L2 ahead of the one-day-ahead register loads
+  const int pfd = WANT_P ? 0 : P.bwd_prefetch;
+  auto prefetch_day = [&](int k) {
+    const int pos = REV ? (T - 1 - k) : k;
+    const int posn = REV ? (T - 2 - k) : (k + 1);
+    const double *j = tJ.at_day(k);
+#pragma unroll
+    for (int q = 0; q < MM; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(j + tJ.f(q)));
+    const double *a = tSm.at_day(posn), *c = tSp.at_day(pos);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a + tSm.f(i)));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(c + tSp.f(i)));
+    }
+  };
+  if (pfd > 0)
+    for (int k = T - 3; k >= k0 && k > T - 2 - pfd; --k) prefetch_day(k);
   BwdDay<M> cur;
   if (!WANT_P && T - 2 >= k0) load_day(T - 2, cur);
+  double pre_nxt = nan, prec_nxt = nan;
+  if (T - 2 >= k0) { const int p0 = REV ? 1 : (T - 2); pre_nxt = group_pre(p0); prec_nxt = group_cost(p0); }
 #pragma unroll 1
   for (int k = T - 2; k >= k0; --k) {  // :204
     const int pos = REV ? (T - 1 - k) : k;
     const int posn = REV ? (T - 2 - k) : (k + 1);
+    const double pre_cur = pre_nxt, prec_cur = prec_nxt;
+    if (k > k0) { const int pp = REV ? (T - k) : (k - 1); pre_nxt = group_pre(pp); prec_nxt = group_cost(pp); }
+    if (pfd > 0 && k - pfd >= k0) prefetch_day(k - pfd);
     if (WANT_P) load_day(k, cur);
     double ds[M], sk[M];
 #pragma unroll
@@ -217,7 +247,7 @@ __global__ void __launch_bounds__(64, WANT_P ? 4 : 8) eks_backward_kernel(const 
       for (int i = 0; i < M; ++i) d[(size_t)i * P.S_SMOOTH.stride] = ss[i];
     }
     // :229 re-run the state equation's input stage on the smoothed state
-    if (!LEG) emit_inputs(pos, in.u + (size_t)pos * in.u_ts, in.u_js, (M == 6) ? ss[M - 1] : 0.0, true);
+    if (!LEG) emit_inputs(pos, in.u + (size_t)pos * in.u_ts, in.u_js, (M == 6) ? ss[M - 1] : 0.0, pre_cur, prec_cur);
   }
   if (WANT_P && P.P_first.p)
     store_mat<M, false>(Ps, P.P_first.p + (size_t)P.P_first.off + b, (size_t)P.P_first.stride);
@@ -228,6 +258,7 @@ static void launch_bwd_model(const EkfParams &p, cudaStream_t st, bool want_p) {
   const int block = (model_dim(MODEL) == 6) ? 32 : 64;
   const int grid = (p.B + block - 1) / block;
   if (want_p) eks_backward_kernel<MODEL, true, TILED><<<grid, block, 0, st>>>(p);
+  else if (p.bwd_prefetch > 0 && model_dim(MODEL) == 6) eks_backward_kernel<MODEL, false, TILED, true><<<grid, block, 0, st>>>(p);
   else        eks_backward_kernel<MODEL, false, TILED><<<grid, block, 0, st>>>(p);
 }
 

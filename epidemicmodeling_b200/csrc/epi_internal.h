@@ -51,6 +51,7 @@ struct EkfParams {
   int k0;                          // first day the smoother needs (0 = all).  Lean sweeps (tiled only):
                                    // the tape holds days k0..T-1, gains/backward run for k >= k0
   int fwd_segments;                // > 1: time-segmented persistent forward launch (m = 6 generic, tiled, no monitor)
+  int bwd_prefetch;                // > 0: the backward recursion pulls the tape page of day k - bwd_prefetch into L2 (small batches)
   int *fwd_sync;                   //      [1 + tiles] ints, zeroed: item counter, per-tile finished segments
   TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1-k0][m*m][32]
   const double *dot_grp;           // per group [T]: input term of days without NaN inputs (NaN = per trajectory)

@@ -220,14 +220,25 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   double a0 = 0.0, a1 = 0.0;
   if (want_cost) {
     if (U_KIND == 2) {
+      // the sums keep their day order; the loads are issued eight days at a time (each day's scalar sits in its
+      // own 256-byte line of the tape: one L2/HBM latency per day when loaded where it is consumed)
+      constexpr int PF = 8;
       const double *nh = P.newcases_hist + (size_t)g * P.T_hist;
-      for (int t = 0; t < P.T_hist; ++t) a0 += nh[t];
-      if (P.hist_cost_grp) {  // lean sweep: the history is given, its day costs are per group
-        const double *hc = P.hist_cost_grp + (size_t)g * P.T_total;
-        // (the last day of the run is never a "given" day: u_opt_smooth(:,T) = 0, written by eks_backward)
-        for (int t = 0; t < P.T_hist; ++t) a1 += (t == P.T_total - 1) ? costp[(size_t)t * cs] : hc[t];
-      } else {
-        for (int t = 0; t < P.T_hist; ++t) a1 += costp[(size_t)t * cs];
+      const bool lean_hist = P.hist_cost_grp != nullptr;  // lean sweep: the history is given, its day costs are per group
+      const double *hc = lean_hist ? P.hist_cost_grp + (size_t)g * P.T_total : nullptr;
+      for (int t0 = 0; t0 < P.T_hist; t0 += PF) {
+        double vn[PF], vc[PF];
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+          const int t = t0 + q;
+          const bool in = t < P.T_hist;
+          vn[q] = in ? __ldg(nh + t) : 0.0;
+          // (the last day of the run is never a "given" day: u_opt_smooth(:,T) = 0, written by eks_backward)
+          vc[q] = !in ? 0.0 : (lean_hist && t != P.T_total - 1) ? __ldg(hc + t) : costp[(size_t)t * cs];
+        }
+#pragma unroll
+        for (int q = 0; q < PF; ++q)
+          if (t0 + q < P.T_hist) { a0 += vn[q]; a1 += vc[q]; }
       }
     } else {
       a0 = P.j0_prefix ? P.j0_prefix[g] : 0.0;
@@ -243,11 +254,26 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   const unsigned key0 = (unsigned)P.seed, key1 = (unsigned)(P.seed >> 32);
   unsigned lvl[EPI_LMAX];
   const double *__restrict__ nz = P.noise.p ? P.noise.p + P.noise.off + b : nullptr;
+  // sweep: the per-day scalars of the next kRing days are kept in registers ahead of the state recursion
+  constexpr int kRing = 8;
+  double rd[kRing], rc[kRing];
+  if (U_KIND == 2) {
+#pragma unroll
+    for (int q = 0; q < kRing; ++q) {
+      rd[q] = (q < K) ? dotp[(size_t)(Th + q) * ds] : 0.0;
+      rc[q] = (q < K && costp) ? costp[(size_t)(Th + q) * cs] : 0.0;
+    }
+  }
   for (int t = 0; t < K; ++t) {  // :24-28
     double dot, cday = 0.0;
     if (U_KIND == 2) {
-      dot = dotp[(size_t)(Th + t) * ds];
-      if (costp) cday = costp[(size_t)(Th + t) * cs];
+      dot = rd[0];
+      cday = rc[0];
+#pragma unroll
+      for (int q = 0; q + 1 < kRing; ++q) { rd[q] = rd[q + 1]; rc[q] = rc[q + 1]; }
+      const int tn = t + kRing;
+      rd[kRing - 1] = (tn < K) ? dotp[(size_t)(Th + tn) * ds] : 0.0;
+      rc[kRing - 1] = (tn < K && costp) ? costp[(size_t)(Th + tn) * cs] : 0.0;
     } else {
       dot = 0.0;
       const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
