@@ -468,6 +468,10 @@ void launch_ekf_forward(const EkfParams &p, cudaStream_t st) {
     launch_ekf_forward_rows(p, st);
     return;
   }
+  if (pair_forward_wanted(p)) {   // small batch: two warps per tile (csrc/ekf_pair.cu)
+    launch_ekf_forward_pair(p, st);
+    return;
+  }
   if (p.fwd_segments > 1 && p.fwd_sync && p.tiled && !monitor) {
     bool done = false;
 #define CALL(MDL) done = launch_fwd_segmented<MDL>(p, st)

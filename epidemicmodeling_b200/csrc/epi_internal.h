@@ -81,6 +81,9 @@ void launch_eks_backward_rows(const EkfParams &p, cudaStream_t st);
 bool rows_forward_ok(const EkfParams &p);
 bool rows_backward_ok(const EkfParams &p);
 bool rows_wanted(long long B, bool forward);
+// two warps per tile (csrc/ekf_pair.cu): the forward pass of small batches of the sweep's call shape
+void launch_ekf_forward_pair(const EkfParams &p, cudaStream_t st);
+bool pair_forward_wanted(const EkfParams &p);
 
 struct SeirpParams {
   int B, K, rate_mode, saturated, out_mode;

@@ -1152,3 +1152,38 @@ def test_lane_group_kernels_are_bit_identical(engine, shape, monkeypatch):
     g_one = call()
     for k in ("S_SMOOTH", "u_opt_smooth"):
         assert_bits(g_rows[k], g_one[k], f"lane-group generic entry {k}")
+
+
+@pytest.mark.parametrize("shape", [(3, 15, 33, 21), (2, 7, 1, 9), (1, 4, 12, 0), (2, 33, 20, 6)])
+def test_two_warp_forward_is_bit_identical(engine, shape, monkeypatch):
+    """csrc/ekf_pair.cu: the forward pass of small batches with two warps per 32-trajectory tile (each warp owns three
+    rows of P, five shared-memory exchanges per day) -- the same bits as the one-warp kernel: full and lean sweeps,
+    ragged tiles, days without observation, and the generic entry with a per-trajectory epsilon."""
+    nR, nE, Th, Tf = shape
+    inp, eps = cases.sweep_case(n_regions=nR, n_eps=nE, T_hist=Th, T_fore=Tf)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    kw = dict(want_front=True, want_u_fore=True, want_u_knee=True)
+    monkeypatch.setenv("EPI_PAIR", "0")
+    monkeypatch.setenv("EPI_FWD_SEGMENTS", "1")
+    one = wl.run_sweep(engine, batch, eps, want_P_first=True, **kw)
+    monkeypatch.setenv("EPI_PAIR", "1")
+    two = wl.run_sweep(engine, batch, eps, want_P_first=True, **kw)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee", "P_first"):
+        assert_bits(two[k], one[k], f"two-warp forward {k} {shape}")
+    lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
+    for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+        assert_bits(lean[k], one[k], f"two-warp forward lean {k} {shape}")
+    c = cases.ekf6_case(1, T_hist=30, T_fore=11)
+    ee = np.array([1e-9, 1e-3, 0.05, 0.3, 0.7, 0.999, 0.2])
+    T, L = c["u"].shape[1], 12
+    cm = lambda P: np.ascontiguousarray(np.asarray(P).T).ravel()
+    call = lambda: engine.ekf_eks(K.MODEL_OPTCTRL, pack_params([c["params"]], L), c["u"].T.copy(), c["x"], c["R_v"],
+                                  cm(c["Q_w"]), c["s_init"], cm(c["Ps_init"]), c["s_final"], cm(c["Ps_final"]),
+                                  B=ee.size, T=T, L=L, G=ee.size, epsilon=ee, r_mode=K.R_PERDAY, fixed_R=False,
+                                  beta=1.0, gamma=0.995, W=21, outputs=("S_SMOOTH", "P_SMOOTH", "u_opt_smooth"), want_status=True)
+    g_two = call()
+    monkeypatch.setenv("EPI_PAIR", "0")
+    g_one = call()
+    for k in ("S_SMOOTH", "P_SMOOTH", "u_opt_smooth", "status"):
+        assert_bits(g_two[k], g_one[k], f"two-warp forward, generic entry {k}")
