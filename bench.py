@@ -40,6 +40,8 @@ BYTES_FUSED_M6 = 864.0            # packed tape written once + read once
 KERNEL_ALGO = {                   # per trajectory-day: (algorithmic bytes, canonical flops)
     "ekf_forward": (432.0, 2314.0),   # tape write (S-, S+, packed P-, P+)
     "eks_gain": (384.0, 1310.0),      # tape read: packed P-, P+ and S+ (S- is the backward pass's); P+A' + pinv + product + Jacobian
+    "ekf_forward_piped": (432.0, 2314.0),  # small shards: the forward pass with the gains of its finished chunks beside it
+    "eks_gain_tail": (0.0, 0.0),           # ... and what is left of the gains when it ends (csrc/capi.cu, piped schedule)
     "eks_backward": (48.0, 204.0),    # S- read; S_SMOOTH recursion + schedule; P_SMOOTH is not needed for (J0, J1)
     "rollout_cost": (0.0, 91.0),
     "pareto": (0.0, 0.0),
@@ -438,9 +440,12 @@ def main():
                   "regions_per_rank": [wl.shard_regions(nR, world, r)[1] - wl.shard_regions(nR, world, r)[0] for r in range(world)],
                   "tiles_per_rank": (per * nE + 31) // 32,
                   "kernel_ms_per_rank": kt_all,
-                  "limiter": "the time-sequential passes: ekf_forward walks T days per trajectory with one warp per 32 "
-                             "trajectories, so a shard of %d tiles on 148 SMs is latency- not throughput-bound; the smoother "
-                             "tail (all-gather + Pareto) is the fixed floor" % ((per * nE + 31) // 32)}
+                  "schedule": ("piped: eks_gain runs on a second stream beside ekf_forward, chunk by chunk behind a stream wait "
+                               "on the forward pass's progress counter; eks_gain_tail is what is left when the forward pass ends")
+                              if any("ekf_forward_piped" in (k_ or {}) for k_ in kt_all) else "one stream",
+                  "limiter": "the time-sequential passes: ekf_forward and eks_backward walk the T days of a trajectory with one "
+                             "warp per 32 trajectories (about 2 us and 1 us a day), so a shard of %d tiles on 148 SMs is latency- "
+                             "not throughput-bound; the smoother tail (all-gather + Pareto) is the fixed floor" % ((per * nE + 31) // 32)}
 
     # extra (not the headline): the lean sweep mode -- identical outputs, smoother only on the days
     # whose schedule is optimised (include/epi_b200.h: epi_sweep_args.lean)

@@ -62,6 +62,13 @@ struct epi_ctx {
   // (EPI_ERR_* code); it is reported by the next epi_sync or the next call on the context.
   int *deferred_err = nullptr;      // pinned, device-mapped
   int *deferred_err_dev = nullptr;
+  // piped schedule of small sweeps (forward || gains): second stream, fork/join events, the driver's stream wait on a
+  // device word (cuStreamWaitValue32, fetched through the runtime so the library needs no link against libcuda)
+  cudaStream_t pipe_stream = nullptr;
+  cudaEvent_t pipe_ev[2] = {nullptr, nullptr};
+  void *wait_value32 = nullptr;
+  int pipe_state = 0;               // 0 untried, 1 ready, -1 unavailable
+  int n_sms = 0;
 };
 
 namespace {
@@ -106,6 +113,28 @@ struct PhaseScope {
     c->phases.push_back(ph);
   }
 };
+
+// cuStreamWaitValue32(stream, addr, value, flags): flags 1 = CU_STREAM_WAIT_VALUE_GEQ
+typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned, unsigned);
+bool pipe_ready(epi_ctx *c) {
+  if (c->pipe_state == 0) {
+    c->pipe_state = -1;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess && fn &&
+        cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking) == cudaSuccess) {
+      cudaEventCreateWithFlags(&c->pipe_ev[0], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&c->pipe_ev[1], cudaEventDisableTiming);
+      cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
+      c->wait_value32 = fn;
+      c->pipe_state = 1;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return c->pipe_state == 1;
+}
 
 void trim_cache(epi_ctx *c) {
   if (c->free_blocks.empty()) return;
@@ -379,6 +408,12 @@ extern "C" void epi_destroy(epi_ctx *c) {
     cudaStreamDestroy(c->copy_stream);
     cudaEventDestroy(c->copy_ev[0]);
     cudaEventDestroy(c->copy_ev[1]);
+  }
+  if (c->pipe_stream) {
+    cudaStreamSynchronize(c->pipe_stream);
+    cudaStreamDestroy(c->pipe_stream);
+    cudaEventDestroy(c->pipe_ev[0]);
+    cudaEventDestroy(c->pipe_ev[1]);
   }
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->deferred_err) cudaFreeHost(c->deferred_err);
@@ -1168,6 +1203,52 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
           CK(cudaMemsetAsync(p.fwd_sync, 0, (size_t)(tiles + 1) * sizeof(int), c->stream));
         }
       }
+      // small shard (a region block of the strong-scaling sweep): forward || gains, see csrc/ekf_forward.cu
+      bool piped = false;
+      int want = 1;  // EPI_PIPE: 0 = one-stream schedule, 2 = the piped kernels one after the other (tuning experiments)
+      {
+        if (const char *e = getenv("EPI_PIPE")) want = atoi(e);
+        piped = want != 0 && Tn > 1 && pipe_ready(c) && forward_piped_ok(p, c->n_sms);
+      }
+      if (piped) {
+        p.pipe_chunks = 8;
+        if (const char *e = getenv("EPI_PIPE_CHUNKS")) p.pipe_chunks = atoi(e) > 0 ? atoi(e) : 8;
+        if (p.pipe_chunks > 64) p.pipe_chunks = 64;
+        p.pipe_sync = (unsigned *)w.dalloc((size_t)p.pipe_chunks * sizeof(unsigned));
+        const unsigned tiles = (unsigned)((nb + 31) / 32);
+        CK(cudaMemsetAsync(p.pipe_sync, 0, (size_t)p.pipe_chunks * sizeof(unsigned), c->stream));
+        CK(cudaEventRecord(c->pipe_ev[0], c->stream));        // fork: the counters are zero, the inputs in place
+        CK(cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[0], 0));
+        {
+          PhaseScope ph(c, "ekf_forward_piped");  // (beside the gains of the chunks it has finished)
+          launch_ekf_forward_piped(p, c->stream);
+          check_launch(c, 1);
+          ph.end();
+        }
+        PhaseScope ph(c, "eks_gain_tail");  // on the launching stream: what is left of the gains when the forward pass ends
+        try {
+        for (int ch = 0; ch < p.pipe_chunks; ++ch) {
+          int kb = 0, ke = 0;
+          pipe_chunk_days(p, ch, kb, ke);
+          EkfParams g = p;
+          g.gk_lo = kb < k0 ? k0 : kb;
+          g.gk_hi = ke < T - 1 ? ke : T - 1;
+          if (g.gk_hi <= g.gk_lo) continue;
+          // all tiles have left chunk ch: the tape holds P-(k + 1), P+(k), S+(k) for every k < ke
+          if (want == 2) { launch_eks_gain(g, c->stream); check_launch(c, 1); continue; }
+          if (((WaitValue32Fn)c->wait_value32)(c->pipe_stream, (unsigned long long)(uintptr_t)(p.pipe_sync + ch), tiles, 1u) != 0)
+            throw EpiError{EPI_ERR_CUDA, "cuStreamWaitValue32 failed"};
+          launch_eks_gain(g, c->pipe_stream);
+          check_launch(c, 1);
+        }
+        } catch (...) {  // never leave the second stream parked on a counter: release every queued wait
+          cudaMemsetAsync(p.pipe_sync, 0xff, (size_t)p.pipe_chunks * sizeof(unsigned), c->stream);
+          throw;
+        }
+        CK(cudaEventRecord(c->pipe_ev[1], c->pipe_stream));   // join
+        CK(cudaStreamWaitEvent(c->stream, c->pipe_ev[1], 0));
+        ph.end();
+      } else {
       {
         PhaseScope ph(c, "ekf_forward");
         launch_ekf_forward(p, c->stream);
@@ -1179,6 +1260,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         launch_eks_gain(p, c->stream);
         check_launch(c, 1);
         ph.end();
+      }
       }
       if (wts_deferred) {  // first consumer of the weights and of cost_grp
         CK(cudaStreamWaitEvent(c->stream, c->copy_ev[1], 0));

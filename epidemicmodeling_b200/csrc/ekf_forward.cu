@@ -139,7 +139,9 @@ EPI_DI void forward_days(const EkfParams &P, const int b, const int k_begin, con
   };
   double x_nxt = 0.0, R_nxt = 0.0, pre_nxt = 0.0;
   if (k_begin < k_end) { x_nxt = day_x(k_begin); R_nxt = LEG ? 0.0 : day_R(k_begin); pre_nxt = day_pre(k_begin); }
+  const bool day_sync = P.day_sync != 0;
   for (int k = k_begin; k < k_end; ++k) {
+    if (day_sync) __syncthreads();  // piped schedule: the four warps of a CTA walk the loop body in step
     const int pos = REV ? (T - 1 - k) : k;
     const double x_cur = x_nxt, R_cur = R_nxt, pre_cur = pre_nxt;
     if (k + 1 < k_end) { x_nxt = day_x(k + 1); R_nxt = LEG ? 0.0 : day_R(k + 1); pre_nxt = day_pre(k + 1); }
@@ -451,6 +453,78 @@ static bool launch_fwd_segmented(const EkfParams &p, cudaStream_t st) {
   } else {
     return false;
   }
+}
+
+// ---- piped schedule (small batches of the sweep: a region shard of the strong-scaling form) ------------------------
+// A shard of a few hundred tiles is latency-bound in this pass (one warp walks the T days of its tile at ~2 us a day
+// whatever else the GPU does) and leaves most SMs idle, while the gains of day k only need the tape up to day k + 1.
+// Here the pass runs as CTAs of 3 to 6 warps (one tile each) that ask for so much dynamic shared memory that no gain
+// CTA fits beside them: a forward warp that shares its scheduler with gain warps takes 5 us a day instead of 2
+// (measured).  The FP64 pipe is shared by the sub-partitions of an SM, so the pass itself slows down with
+// the warps per SM (1.11 ms spread thin, 1.42 at 4 per SM, 1.8 at 6): pipe_warps picks the smallest CTA that leaves
+// about half of the SMs to the gains.  After every time chunk a warp publishes its progress (tape stores, fence,
+// one atomic per tile); the host has queued the gains of that chunk on a second stream behind a stream wait on the
+// counter, so they fill the SMs the forward pass does not occupy.  Same forward_days, same bits.
+constexpr int kPipeMaxWarps = 6;
+constexpr size_t kPipeSmem = 200 * 1024;  // + one gain CTA's 48 KB exceeds an SM's 227 KB
+
+void pipe_chunk_days(const EkfParams &p, int c, int &kb, int &ke) {
+  const int S = p.pipe_chunks, T = p.T, k0 = p.k0;
+  kb = (c == 0) ? 0 : k0 + (int)(((long long)(T - k0) * c) / S);
+  ke = (c + 1 == S) ? T : k0 + (int)(((long long)(T - k0) * (c + 1)) / S);
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(32 * kPipeMaxWarps, 1) ekf_forward_piped_kernel(const __grid_constant__ EkfParams P) {
+  const int S = P.pipe_chunks, T = P.T, k0 = P.k0;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (tile >= (P.B + 31) / 32) return;
+  // lanes without a trajectory leave the KERNEL here (not just forward_days): the per-day CTA barrier counts the
+  // threads that have not exited
+  const unsigned mask = __ballot_sync(0xffffffffu, tile * 32 + lane < P.B);
+  if (tile * 32 + lane >= P.B) return;
+  for (int c = 0; c < S; ++c) {
+    const int kb = (c == 0) ? 0 : k0 + (int)(((long long)(T - k0) * c) / S);
+    const int ke = (c + 1 == S) ? T : k0 + (int)(((long long)(T - k0) * (c + 1)) / S);
+    if (ke > kb || c == 0) forward_days<MODEL, false, true, true>(P, tile * 32 + lane, kb, ke, nullptr);
+    __threadfence();
+    __syncwarp(mask);
+    if (lane == 0) atomicAdd(P.pipe_sync + c, 1u);
+  }
+}
+
+// warps (tiles) per CTA: measured on 148 SMs, ms per step for 3 / 4 / 6 warps (one-stream schedule beside it):
+// 235 tiles 2.45 / 2.48 / 2.62 (2.70), 461 tiles - / 3.62 / 3.53 (3.70).  0 = the batch is too large to pipe.
+static int pipe_warps(int tiles, int n_sms) {
+  if (const char *e = getenv("EPI_PIPE_WARPS")) {
+    const int w = atoi(e);
+    return (w >= 1 && w <= kPipeMaxWarps && (tiles + w - 1) / w <= n_sms - n_sms / 10) ? w : 0;
+  }
+  for (int w : {3, 4, 6})
+    if ((tiles + w - 1) / w <= (n_sms * 11) / 20) return w;
+  return 0;
+}
+
+bool forward_piped_ok(const EkfParams &p, int n_sms) {
+  const bool monitor = (p.rho.p != nullptr) || (p.beta != 1.0);
+  // the call shape of the sweep, enough days to cut, and about half of the SMs left for the gains
+  return p.model == EPI_MODEL_OPTCTRL && p.tiled && !monitor && forward_plain(p) && p.T - p.k0 >= 64 && p.B > 0 &&
+         pipe_warps((p.B + 31) / 32, n_sms) > 0;
+}
+
+void launch_ekf_forward_piped(const EkfParams &p, cudaStream_t st) {
+  int dev = 0, n_sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = (p.B + 31) / 32, kPipeWarps = pipe_warps(tiles, n_sms), ctas = (tiles + kPipeWarps - 1) / kPipeWarps;
+  auto kern = ekf_forward_piped_kernel<EPI_MODEL_OPTCTRL>;
+  size_t smem = kPipeSmem;
+  if (const char *e = getenv("EPI_PIPE_SMEM_KB")) smem = (size_t)atoi(e) * 1024;  // tuning experiments
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  EkfParams q = p;
+  q.day_sync = 0;  // a CTA barrier per day, so that the warps share their instruction lines: 1.50 against 1.42 ms
+  if (const char *e = getenv("EPI_PIPE_DAYSYNC")) q.day_sync = atoi(e);
+  kern<<<ctas, 32 * kPipeWarps, smem, st>>>(q);
 }
 
 int forward_resident_slots6() {

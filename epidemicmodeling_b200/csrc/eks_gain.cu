@@ -53,15 +53,17 @@ __global__ void __launch_bounds__(EPI_GAIN_BLOCK, EPI_GAIN_MIN_BLOCKS) eks_gain_
   const size_t Bpad = (size_t)((P.B + 31) / 32) * 32;  // every warp = one 32-trajectory tile
   const int T = P.T, L = P.L;
   const int k0 = P.k0;
-  if (tid >= (size_t)(T - 1 - k0) * Bpad) return;
+  // days of this launch: all of k0 .. T-2, or the [gk_lo, gk_hi) of one time chunk of the piped schedule
+  const int klo = (P.gk_hi > P.gk_lo) ? P.gk_lo : k0, khi = (P.gk_hi > P.gk_lo) ? P.gk_hi : T - 1;
+  if (tid >= (size_t)(khi - klo) * Bpad) return;
 #ifndef EPI_GAIN_TILE_MAJOR
   // consecutive warps (and CTAs) = consecutive days of ONE tile: their tape pages are contiguous in the
   // [tile][day][field][32] scratch layout (6.38 -> 6.20 ms against the tile-major order below)
-  const size_t wid = tid >> 5, nd = (size_t)(T - 1 - k0);
-  const int k = k0 + (int)(wid % nd);
+  const size_t wid = tid >> 5, nd = (size_t)(khi - klo);
+  const int k = klo + (int)(wid % nd);
   const int b = (int)((wid / nd) * 32 + (tid & 31));
 #else
-  const int k = k0 + (int)(tid / Bpad);
+  const int k = klo + (int)(tid / Bpad);
   const int b = (int)(tid % Bpad);
 #endif
   // lanes of this warp that hold a trajectory (the pair-at-a-time pinv is warp-synchronous)
@@ -217,7 +219,8 @@ template <int MODEL>
 static void launch_gain_model(const EkfParams &p, cudaStream_t st) {
   if (p.T - p.k0 < 2) return;
   const size_t Bpad = (size_t)((p.B + 31) / 32) * 32;
-  const size_t total = (size_t)(p.T - 1 - p.k0) * Bpad;
+  const size_t total = (size_t)((p.gk_hi > p.gk_lo) ? (p.gk_hi - p.gk_lo) : (p.T - 1 - p.k0)) * Bpad;
+  if (total == 0) return;
   const int block = EPI_GAIN_BLOCK;
   const unsigned grid = (unsigned)((total + block - 1) / block);
   constexpr int M = model_dim(MODEL);

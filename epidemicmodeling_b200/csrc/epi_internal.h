@@ -53,6 +53,13 @@ struct EkfParams {
   int fwd_segments;                // > 1: time-segmented persistent forward launch (m = 6 generic, tiled, no monitor)
   int bwd_prefetch;                // > 0: the backward recursion pulls the tape page of day k - bwd_prefetch into L2 (small batches)
   int *fwd_sync;                   //      [1 + tiles] ints, zeroed: item counter, per-tile finished segments
+  // forward || gains for small batches ("piped schedule"): the forward kernel counts the tiles that have
+  // finished time chunk c in pipe_sync[c]; the gains of the days [gk_lo, gk_hi) are launched on a second stream behind
+  // a stream wait on that word.  gk_lo == gk_hi == 0: the gain launch covers all days k0 .. T-2.
+  int pipe_chunks;
+  int day_sync;                    //      1: the warps of a forward CTA meet at a barrier every day (instruction lines shared)
+  unsigned *pipe_sync;             //      [pipe_chunks] words, zeroed
+  int gk_lo, gk_hi;
   TArr J;                          // scratch smoother gains, always tiled: [b/32][T-1-k0][m*m][32]
   const double *dot_grp;           // per group [T]: input term of days without NaN inputs (NaN = per trajectory)
   const double *cost_grp;          // per group [T]: that day's sum_j w*u (sweep), or null
@@ -74,6 +81,10 @@ void launch_ekf_forward(const EkfParams &p, cudaStream_t st);
 int forward_segments(long long tiles, int slots);  // segment count minimising the idle tail (1 = plain launch)
 int forward_resident_slots6();                     // resident one-warp CTAs of the m = 6 forward kernel on this device
 void launch_eks_gain(const EkfParams &p, cudaStream_t st);
+// piped schedule: four tiles per CTA, one warp per SM sub-partition, the SM kept to itself (csrc/ekf_forward.cu)
+bool forward_piped_ok(const EkfParams &p, int n_sms);
+void launch_ekf_forward_piped(const EkfParams &p, cudaStream_t st);
+void pipe_chunk_days(const EkfParams &p, int c, int &kb, int &ke);  // days [kb, ke) of time chunk c
 void launch_eks_backward(const EkfParams &p, cudaStream_t st);
 // lane-group forms (csrc/ekf_rows.cu): six lanes per trajectory, for small batches of the sweep's call shape
 void launch_ekf_forward_rows(const EkfParams &p, cudaStream_t st);

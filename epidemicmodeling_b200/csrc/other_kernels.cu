@@ -375,7 +375,11 @@ EPI_DI double stage_value(const double *p) { return *p; }
 // SIMPLE: the Monte-Carlo scoring shape -- costs only (no trajectory outputs), no noise array.
 // NST: stages of the shared-memory ring (a stage is re-filled as soon as the CTA has consumed it, so NST - 1
 // stages are in flight while one is being integrated)
-template <int U_KIND, int SB, int TT, int LC, bool SIMPLE, int NST>
+// CPA: the stage is filled with 16-byte cp.async (LDGSTS) issued by every thread instead of one bulk copy per row.
+// A uint8 row piece is only SB = 256 bytes, and the TMA unit of an SM retires about one bulk operation per 46 cycles
+// whatever its size: 33 M row pieces per 5.9 M-trajectory wave are 5.3 ms of TMA issue on 148 SMs -- the r02 capture's
+// 68 % of stall samples in the stage wait at 13 % of DRAM.  The same bytes are 12 LDGSTS per thread and stage.
+template <int U_KIND, int SB, int TT, int LC, bool SIMPLE, int NST, bool CPA>
 __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constant__ RolloutParams P) {
   using U = typename std::conditional<U_KIND == EPI_U_U8, unsigned char, double>::type;
   extern __shared__ __align__(128) unsigned char stage_raw[];  // [NST][TT][L][SB] of U
@@ -393,12 +397,35 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
   const size_t us = (size_t)P.u_stride;
   const int n_stages = (K + TT - 1) / TT;
 
-  if (tid == 0) {
+  if (!CPA) {
+    if (tid == 0) {
 #pragma unroll
-    for (int q = 0; q < NST; ++q) mbar_init(&bars[q], 1);
+      for (int q = 0; q < NST; ++q) mbar_init(&bars[q], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
+  // cp.async form: every thread copies chunks tid, tid + SB, ... of the stage (row = chunk / CPR, 16-byte piece =
+  // chunk % CPR) and commits ONE group per stage, empty when the stage does not exist, so that group counts line up
+  auto issue_cpa = [&](int sidx) {
+    if (sidx < n_stages) {
+      constexpr int CPR = (int)(SB * sizeof(U) / 16);  // chunks per row
+      const int t0 = sidx * TT;
+      const int nt = (K - t0 < TT) ? (K - t0) : TT;
+      const int chunks = nt * L * CPR;
+      const int ncp = (int)(nb * sizeof(U) / 16);  // chunks of a row that exist (last CTA)
+      unsigned char *dst = reinterpret_cast<unsigned char *>(stage_u + (size_t)(sidx % NST) * stage_elems);
+      const unsigned char *src = reinterpret_cast<const unsigned char *>(gu + (size_t)t0 * L * us);
+      for (int c = tid; c < chunks; c += SB) {
+        const int r = c / CPR, pc = c % CPR;
+        if (pc < ncp)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (size_t)c * 16)),
+                       "l"(src + (size_t)r * us * sizeof(U) + (size_t)pc * 16)
+                       : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   auto issue = [&](int sidx) {  // executed by warp 0
     const int t0 = sidx * TT;
     const int nt = (K - t0 < TT) ? (K - t0) : TT;
@@ -410,7 +437,10 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
     for (int r = tid; r < rows; r += 32)
       bulk_load_row(dst + (size_t)r * SB, gu + ((size_t)t0 * L + r) * us, (unsigned)(nb * sizeof(U)), bar);
   };
-  if (tid < 32) {
+  if (CPA) {
+#pragma unroll
+    for (int q = 0; q < NST; ++q) issue_cpa(q);
+  } else if (tid < 32) {
     for (int q = 0; q < NST && q < n_stages; ++q) issue(q);
   }
 
@@ -441,9 +471,15 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
     const int nt = (K - t0 < TT) ? (K - t0) : TT;
     if (w_tiled) {
       for (int q = tid; q < nt * L; q += SB) wtile[q] = __ldg(P.w + ((size_t)g_first * K + t0) * L + q);
-      __syncthreads();
+      if (!CPA) __syncthreads();
     }
-    mbar_wait(&bars[sidx % NST], (unsigned)((sidx / NST) & 1));
+    if (CPA) {
+      // this thread's chunks of stage sidx have landed once at most NST - 1 younger groups are pending
+      asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");
+      __syncthreads();  // ... and everybody else's (and wtile)
+    } else {
+      mbar_wait(&bars[sidx % NST], (unsigned)((sidx / NST) & 1));
+    }
     const U *__restrict__ su = stage_u + (size_t)(sidx % NST) * stage_elems + tid;
     // the input term and the day's weighted cost do not depend on the state: evaluate them for DQ
     // days at once (independent FMA chains = instruction-level parallelism), then run the DQ
@@ -510,7 +546,8 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
       else run_tile(std::false_type{});
     }
     __syncthreads();  // everyone is done reading this buffer
-    if (tid < 32 && sidx + NST < n_stages) issue(sidx + NST);
+    if (CPA) issue_cpa(sidx + NST);
+    else if (tid < 32 && sidx + NST < n_stages) issue(sidx + NST);
   }
   if (want_cost && active) {
     P.J0.p[P.J0.off + b] = a0 / (double)P.T_total;                        // NPICost.m:6
@@ -520,8 +557,8 @@ __global__ void __launch_bounds__(SB) rollout_staged_kernel(const __grid_constan
 
 template <int U_KIND>
 static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
-#ifndef EPI_ROLL_SB  // trajectories per CTA = bytes per uint8 row piece of a TMA bulk copy
-#define EPI_ROLL_SB 256
+#ifndef EPI_ROLL_SB  // trajectories per CTA = bytes per uint8 row piece (cp.async: 256 / 128 -> 11.25 / 10.89 ms at half of config 5)
+#define EPI_ROLL_SB 128
 #endif
 #ifndef EPI_ROLL_TT  // days per stage (uint8 schedules)
 #define EPI_ROLL_TT 16
@@ -532,6 +569,10 @@ static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
   constexpr int SB = (U_KIND == EPI_U_U8) ? EPI_ROLL_SB : 256;
   constexpr int TT = (U_KIND == EPI_U_U8) ? EPI_ROLL_TT : 2;
   constexpr int NST = (U_KIND == EPI_U_U8) ? EPI_ROLL_NST : 2;
+#ifndef EPI_ROLL_CPA  // uint8 schedules: stage with 16-byte cp.async (1) or one TMA bulk copy per 256-byte row piece (0)
+#define EPI_ROLL_CPA 1
+#endif
+  constexpr bool CPA = (U_KIND == EPI_U_U8) && (EPI_ROLL_CPA != 0);
   const size_t esz = (U_KIND == EPI_U_U8) ? 1 : 8;
   // TMA bulk copies need 16-byte aligned, 16-byte multiple rows
   if (p.K < 1 || p.B < 8 * SB || (((size_t)p.B * esz) & 15) || (((size_t)p.u_stride * esz) & 15) ||
@@ -542,7 +583,7 @@ static bool rollout_launch_staged(const RolloutParams &p, cudaStream_t st) {
   const bool simple = p.J0.p && p.w && !p.noise.p && !p.s.p && !p.i.p && !p.alpha.p;
 #define EPI_LAUNCH_STAGED(LC, SIMPLE)                                                              \
   do {                                                                                             \
-    auto kern = rollout_staged_kernel<U_KIND, SB, TT, LC, SIMPLE, NST>;                                 \
+    auto kern = rollout_staged_kernel<U_KIND, SB, TT, LC, SIMPLE, NST, CPA>;                                 \
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     kern<<<grid, SB, smem, st>>>(p);                                                               \
   } while (0)

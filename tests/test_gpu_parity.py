@@ -1187,3 +1187,26 @@ def test_two_warp_forward_is_bit_identical(engine, shape, monkeypatch):
     g_one = call()
     for k in ("S_SMOOTH", "P_SMOOTH", "u_opt_smooth", "status"):
         assert_bits(g_two[k], g_one[k], f"two-warp forward, generic entry {k}")
+
+
+@pytest.mark.parametrize("shape", [(3, 15, 60, 30), (2, 40, 50, 70), (1, 33, 100, 12)])
+def test_piped_schedule_is_bit_identical(engine, shape, monkeypatch):
+    """Small sweeps run forward || gains (csrc/ekf_forward.cu `ekf_forward_piped_kernel`, capi.cu): the forward pass as
+    4-warp CTAs that keep their SM, the gains of a time chunk on a second stream behind a stream wait on the forward
+    pass's progress counter.  Same bits as the one-stream schedule: full and lean sweeps, ragged tiles, 1..9 chunks."""
+    nR, nE, Th, Tf = shape
+    inp, eps = cases.sweep_case(n_regions=nR, n_eps=nE, T_hist=Th, T_fore=Tf)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    kw = dict(want_front=True, want_u_fore=True, want_u_knee=True)
+    monkeypatch.setenv("EPI_PIPE", "0")
+    one = wl.run_sweep(engine, batch, eps, want_P_first=True, **kw)
+    for chunks in ("8", "1", "9"):
+        monkeypatch.setenv("EPI_PIPE", "1")
+        monkeypatch.setenv("EPI_PIPE_CHUNKS", chunks)
+        two = wl.run_sweep(engine, batch, eps, want_P_first=True, **kw)
+        for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee", "P_first"):
+            assert_bits(two[k], one[k], f"piped schedule ({chunks} chunks) {k} {shape}")
+        lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
+        for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+            assert_bits(lean[k], one[k], f"piped schedule ({chunks} chunks) lean {k} {shape}")
