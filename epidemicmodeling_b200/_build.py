@@ -18,7 +18,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libepi_b200.so")
 OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = ["capi.cu", "ekf_forward.cu", "eks_gain.cu", "eks_backward.cu", "ekf_rows.cu", "ekf_pair.cu", "other_kernels.cu", "pareto_sorted.cu", "rt_expfit.cu", "preprocess.cu", "nnls.cu"]
-HEADERS = [os.path.join(CSRC, h) for h in ("epi_device.cuh", "epi_internal.h", "epi_linalg.cuh", "epi_linalg_experiments.cuh", "ekf_common.cuh")] + \
+HEADERS = [os.path.join(CSRC, h) for h in ("epi_device.cuh", "epi_internal.h", "epi_linalg.cuh", "epi_linalg_experiments.cuh", "ekf_common.cuh", "epi_async.cuh")] + \
           [os.path.join(ROOT, "include", "epi_b200.h")]
 NVCC_FLAGS = ["-O3", "--fmad=false", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

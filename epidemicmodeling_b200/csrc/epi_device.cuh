@@ -183,7 +183,9 @@ struct InputPass {
   double a25;   // A(3,6)
   double cost;  // sum_j w_day[j] * u_opt[j]   (NPICost's weights.*inputs for this day)
 };
-template <int MODEL, bool WANT_A25, bool WANT_COST>
+// PRELOAD: the day's inputs and weights are read into registers before the first schedule entry is stored (the stores
+// of u_out otherwise fence the loads into batches: three exposed latencies per day in the small-batch recursion, ncu)
+template <int MODEL, bool WANT_A25, bool WANT_COST, bool PRELOAD = false>
 EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
                             const double *__restrict__ u, size_t u_stride, int L,
                             double *__restrict__ u_out, size_t uo_stride,
@@ -201,10 +203,19 @@ EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
   // not the input turns out to be missing, so no load waits behind the NaN test of the previous NPI --
   // fetched inside that branch they were a chain of twelve exposed memory latencies on every day to
   // optimise (ncu r01) -- and the compiler is free to batch them as far as registers allow.
+  double u_in[PRELOAD ? EPI_LMAX : 1], w_in[(PRELOAD && WANT_COST) ? EPI_LMAX : 1];
+  if (PRELOAD) {
+#pragma unroll
+    for (int j = 0; j < EPI_LMAX; ++j)
+      if (j < L) {
+        u_in[j] = __ldg(u + (size_t)j * u_stride);
+        if (WANT_COST) w_in[j] = __ldg(w_day + j);
+      }
+  }
 #pragma unroll
   for (int j = 0; j < EPI_LMAX; ++j) {
     if (j < L) {
-      double uj = u[(size_t)j * u_stride];
+      double uj = PRELOAD ? u_in[j] : u[(size_t)j * u_stride];
       const double aj = __ldg(&p->a[j]);
       const double umax = __ldg(&p->u_max[j]);
       if (SIX) {
@@ -224,7 +235,7 @@ EPI_DI InputPass input_pass(const ModelConsts &c, double eps, double s5,
       const double d = umax - uj;
       r.dot = (j == 0) ? g * d : fma(g, d, r.dot);
       if (WANT_COST) {
-        const double wu = w_day[j] * uj;
+        const double wu = ((PRELOAD && WANT_COST) ? w_in[j] : w_day[j]) * uj;
         r.cost = (j == 0) ? wu : (r.cost + wu);
       }
       if (u_out) u_out[(size_t)j * uo_stride] = uj;

@@ -52,6 +52,7 @@ struct EkfParams {
                                    // the tape holds days k0..T-1, gains/backward run for k >= k0
   int fwd_segments;                // > 1: time-segmented persistent forward launch (m = 6 generic, tiled, no monitor)
   int bwd_prefetch;                // > 0: the backward recursion pulls the tape page of day k - bwd_prefetch into L2 (small batches)
+  int bwd_stages;                  // > 0: staged backward recursion (small batches): shared-memory ring of this many tape days per tile
   int *fwd_sync;                   //      [1 + tiles] ints, zeroed: item counter, per-tile finished segments
   // forward || gains for small batches ("piped schedule"): the forward kernel counts the tiles that have
   // finished time chunk c in pipe_sync[c]; the gains of the days [gk_lo, gk_hi) are launched on a second stream behind

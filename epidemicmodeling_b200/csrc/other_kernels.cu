@@ -5,6 +5,7 @@
 #include <type_traits>
 
 #include "epi_internal.h"
+#include "epi_async.cuh"
 #include "epi_device.cuh"
 
 namespace epi {
@@ -341,33 +342,6 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
 // (cp.async.bulk global -> shared, mbarrier completion), double buffered: SB-byte /
 // SB*8-byte contiguous rows, fetched while the previous stage is being integrated.
 // ---------------------------------------------------------------------------
-EPI_DI void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
-}
-EPI_DI void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-EPI_DI void mbar_wait(unsigned long long *bar, unsigned parity) {
-  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-  unsigned done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  }
-}
-EPI_DI void bulk_load_row(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          (unsigned)__cvta_generic_to_shared(sdst)),
-      "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-      : "memory");
-}
-
 EPI_DI double stage_value(const unsigned char *p) { return u32_to_double((unsigned)*p); }
 EPI_DI double stage_value(const double *p) { return *p; }
 

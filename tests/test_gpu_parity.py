@@ -1210,3 +1210,25 @@ def test_piped_schedule_is_bit_identical(engine, shape, monkeypatch):
         lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
         for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
             assert_bits(lean[k], one[k], f"piped schedule ({chunks} chunks) lean {k} {shape}")
+
+
+@pytest.mark.parametrize("shape", [(3, 15, 33, 21), (2, 7, 1, 9), (1, 4, 12, 0), (2, 40, 50, 70)])
+def test_staged_backward_is_bit_identical(engine, shape, monkeypatch):
+    """Small sweeps run the smoother recursion with the tape pages streamed by TMA bulk copies into a shared-memory ring
+    (csrc/eks_backward.cu, STAGED): the same bits as the register-prefetch kernel for ring depths 1, 2, 5 and 16 (deeper
+    than the run is long), full and lean sweeps, ragged tiles, a run without history."""
+    nR, nE, Th, Tf = shape
+    inp, eps = cases.sweep_case(n_regions=nR, n_eps=nE, T_hist=Th, T_fore=Tf)
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    kw = dict(want_front=True, want_u_fore=True, want_u_knee=True)
+    monkeypatch.setenv("EPI_BWD_STAGES", "0")
+    one = wl.run_sweep(engine, batch, eps, **kw)
+    for stages in ("1", "2", "5", "16"):
+        monkeypatch.setenv("EPI_BWD_STAGES", stages)
+        two = wl.run_sweep(engine, batch, eps, **kw)
+        for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+            assert_bits(two[k], one[k], f"staged backward ({stages} stages) {k} {shape}")
+        lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
+        for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
+            assert_bits(lean[k], one[k], f"staged backward ({stages} stages) lean {k} {shape}")
