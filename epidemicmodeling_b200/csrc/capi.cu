@@ -1275,7 +1275,10 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
         ph.end();
       }
       RolloutParams r{};
-      r.hist_cost_grp = a->lean ? cost_grp : nullptr;
+      // the cost of a history day whose NPIs are all given is the same for every trajectory of the region: read it per
+      // group (L1) instead of 441 per-trajectory tape lines; days with missing NPIs keep the per-trajectory value
+      r.hist_cost_grp = cost_grp;
+      r.hist_cost_per_traj = a->lean ? 0 : 1;
       r.B = (int)nb; r.K = Tf; r.L = L; r.G = a->n_eps; r.b0 = b0;
       r.prm = prm; r.x0 = x0; r.noise_std = nstd;
       r.u_kind = 2;

@@ -122,7 +122,8 @@ struct RolloutParams {
   const double *j0_prefix, *j1_prefix, *w;    // per group
   const double *newcases_hist;    // sweep: per group [T_hist] (summed in-kernel)
   const double *dot_day, *cost_day;  // sweep: tiled [b/32][T_total][1][32] of this wave
-  const double *hist_cost_grp;       // lean sweep: per group [T_total] day costs of the (given) history
+  const double *hist_cost_grp;       // sweep: per group [T_total] day costs of the history days whose inputs are all given (NaN otherwise)
+  int hist_cost_per_traj;            // 1 (full sweep): a NaN entry falls back to the per-trajectory cost_day written by eks_backward
   TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);

@@ -225,21 +225,37 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       // own 256-byte line of the tape: one L2/HBM latency per day when loaded where it is consumed)
       constexpr int PF = 8;
       const double *nh = P.newcases_hist + (size_t)g * P.T_hist;
-      const bool lean_hist = P.hist_cost_grp != nullptr;  // lean sweep: the history is given, its day costs are per group
-      const double *hc = lean_hist ? P.hist_cost_grp + (size_t)g * P.T_total : nullptr;
-      for (int t0 = 0; t0 < P.T_hist; t0 += PF) {
-        double vn[PF], vc[PF];
+      const bool grp_hist = P.hist_cost_grp != nullptr;  // the day costs of a given history are per group
+      const bool per_traj = !grp_hist || P.hist_cost_per_traj != 0;
+      const double *hc = grp_hist ? P.hist_cost_grp + (size_t)g * P.T_total : nullptr;
+      const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+      auto fetch = [&](int t0, double (&vn)[PF], double (&vc)[PF]) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
           const int t = t0 + q;
           const bool in = t < P.T_hist;
           vn[q] = in ? __ldg(nh + t) : 0.0;
           // (the last day of the run is never a "given" day: u_opt_smooth(:,T) = 0, written by eks_backward)
-          vc[q] = !in ? 0.0 : (lean_hist && t != P.T_total - 1) ? __ldg(hc + t) : costp[(size_t)t * cs];
+          const bool last = (t == P.T_total - 1);
+          double v = (in && grp_hist && !last) ? __ldg(hc + t) : qnan;
+          // the last day, or (full sweep) a day with missing NPIs: the trajectory's own value
+          if (in && (last || per_traj) && !(v == v)) v = costp[(size_t)t * cs];
+          vc[q] = in ? v : 0.0;
         }
+      };
+      auto consume = [&](int t0, const double (&vn)[PF], const double (&vc)[PF]) {
 #pragma unroll
         for (int q = 0; q < PF; ++q)
           if (t0 + q < P.T_hist) { a0 += vn[q]; a1 += vc[q]; }
+      };
+      // two register sets: the loads of the next eight days are in flight while this set is summed
+      double vn0[PF], vc0[PF], vn1[PF], vc1[PF];
+      fetch(0, vn0, vc0);
+      for (int t0 = 0; t0 < P.T_hist; t0 += 2 * PF) {
+        fetch(t0 + PF, vn1, vc1);
+        consume(t0, vn0, vc0);
+        fetch(t0 + 2 * PF, vn0, vc0);
+        consume(t0 + PF, vn1, vc1);
       }
     } else {
       a0 = P.j0_prefix ? P.j0_prefix[g] : 0.0;
@@ -265,16 +281,21 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       rc[q] = (q < K && costp) ? costp[(size_t)(Th + q) * cs] : 0.0;
     }
   }
-  for (int t = 0; t < K; ++t) {  // :24-28
+  // the ring slots are STATIC (the day loop is unrolled over the ring): shifting the ring made every day wait for the
+  // load issued the day before (ncu: 39 % of the small-batch kernel on that move)
+  constexpr int kUnr = (U_KIND == 2) ? kRing : 1;
+  for (int t0 = 0; t0 < K; t0 += kUnr) {  // :24-28
+#pragma unroll
+  for (int tq = 0; tq < kUnr; ++tq) {
+    const int t = t0 + tq;
+    if (t >= K) break;
     double dot, cday = 0.0;
     if (U_KIND == 2) {
-      dot = rd[0];
-      cday = rc[0];
-#pragma unroll
-      for (int q = 0; q + 1 < kRing; ++q) { rd[q] = rd[q + 1]; rc[q] = rc[q + 1]; }
+      dot = rd[tq];
+      cday = rc[tq];
       const int tn = t + kRing;
-      rd[kRing - 1] = (tn < K) ? dotp[(size_t)(Th + tn) * ds] : 0.0;
-      rc[kRing - 1] = (tn < K && costp) ? costp[(size_t)(Th + tn) * cs] : 0.0;
+      rd[tq] = (tn < K) ? dotp[(size_t)(Th + tn) * ds] : 0.0;
+      rc[tq] = (tn < K && costp) ? costp[(size_t)(Th + tn) * cs] : 0.0;
     } else {
       dot = 0.0;
       const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
@@ -326,6 +347,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
       a0 += (S * I) * A;  // s.*i.*alpha (:493)
       a1 += cday;
     }
+  }
   }
   if (want_cost) {
     P.J0.p[P.J0.off + b] = a0 / (double)P.T_total;                        // NPICost.m:6
