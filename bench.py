@@ -689,6 +689,20 @@ def main():
         except Exception as exc:  # the headline line must still be printed
             secondary = {"error": repr(exc)}
 
+    # N > 1: BASELINE config 5 ("random-NPI Monte-Carlo scoring ... at 1/2/4/8 GPUs with Pareto all-gather") sharded by
+    # region, outside the headline timing (tools/bench_configs.py measure_config5_sharded); N = 1 is in `secondary`
+    config5 = None
+    if world > 1 and not a.no_secondary:
+        try:
+            del dbatch
+            torch.cuda.empty_cache()
+            eng.release_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+            config5 = bench_configs.measure_config5_sharded(eng, rank, world, dev)
+        except Exception as exc:
+            config5 = {"error": repr(exc)}
+
     if rank == 0:
         par = ("1 GPU: the whole sweep, Pareto inside epi_sweep" if world == 1 else
                f"strong: {nR} regions sharded in contiguous blocks of {per} over {world} GPUs; per step ONE all-gather of the "
@@ -703,7 +717,7 @@ def main():
                            "mode_value": "EPI_MEM_DEVICE (inputs resident in HBM)",
                            "mode_e2e": "EPI_MEM_HOST (host buffers, blocking call; pinned = headline, pageable beside it)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-                "cpu_baseline": cpu, "strong_scaling": strong, "host_multi_call": host_multi, "replica_weak": replica, "secondary": secondary,
+                "cpu_baseline": cpu, "strong_scaling": strong, "host_multi_call": host_multi, "replica_weak": replica, "secondary": secondary, "config5_sharded": config5,
                 "lean_mode": None if ms_lean is None else {
                               "value": units_total / (ms_lean * 1e-3), "unit": "trajectory-days/s",
                               "ms_per_step": ms_lean, "outputs_bit_identical_to_full": lean_same,

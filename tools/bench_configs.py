@@ -221,6 +221,85 @@ def measure(eng, only=0, scale=1.0, spot_check=True, fp64=None):
     return out
 
 
+
+def measure_config5_sharded(eng, rank, world, dev, steps=5, warm=2, scale=1.0):
+    """BASELINE config 5 at N GPUs (every rank calls this): the 236 regions x 100k random NPI schedules x 120 days are
+    sharded by region (TrainPredictPrescribeNPI.m:421,500 are the loops), every rank draws its schedules in the kernel
+    (Philox counters are global: `first` = the shard's first trajectory, so the job is the same whatever N), scores
+    them (SIalpha_Controlled + NPICost), extracts the Pareto front and knee of each of ITS regions, and one all-gather
+    (two NCCL calls: front masks and knee indices) assembles the per-region fronts on every rank.  Device-timed, max
+    over ranks; rank 0 spot-checks its first and last trajectory against the oracle."""
+    import torch.distributed as dist
+    from epidemicmodeling_b200 import workloads as wl
+    nR, nS, Kn, L = 236, int(100_000 * scale), 120, 12
+    lo, hi = wl.shard_regions(nR, world, rank)
+    per, n_loc = (nR + world - 1) // world, hi - lo
+    reg = syn.load_regions(nR)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    prm = pack_params([dict(dt=1.0, beta=syn.BETA, gamma=syn.GAMMA, b=reg["b"][r], a=reg["a"][r], u_max=reg["npi_max"],
+                            u_min=np.zeros(L), alpha_min=1e-8, alpha_max=100.0) for r in range(lo, hi)], L)
+    prmd = params_to_device(prm, dev)
+    x0 = t(np.array([[(reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0] for r in range(lo, hi)]))
+    w = t(np.stack([np.repeat(reg["cost_weights"][r][None, :], Kn, axis=0) for r in range(lo, hi)]))
+    j0p = torch.zeros(n_loc, dtype=torch.float64, device=dev)
+    j1p = torch.zeros(n_loc, dtype=torch.float64, device=dev)
+    Bm = n_loc * nS
+    send_mask = torch.zeros((per, nS), dtype=torch.uint8, device=dev)
+    send_iopt = torch.zeros((per,), dtype=torch.int32, device=dev)
+    full_mask = torch.empty((world * per, nS), dtype=torch.uint8, device=dev)
+    full_iopt = torch.empty((world * per,), dtype=torch.int32, device=dev)
+    holder = {}
+
+    def step():
+        o = eng.rollout_cost(prmd, x0, None, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True, T_total=Kn,
+                             j0_prefix=j0p, j1_prefix=j1p, w=w, seed=5, first=lo * nS)
+        eng.pareto(o["J0"].view(n_loc, nS), o["J1"].view(n_loc, nS), out=(send_mask[:n_loc], send_iopt[:n_loc]))
+        dist.all_gather_into_tensor(full_mask, send_mask)
+        dist.all_gather_into_tensor(full_iopt, send_iopt)
+        holder["o"] = o
+
+    for _ in range(warm):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    tm = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    kt = {k: round(v, 4) for k, v in eng.last_kernel_times().items()}   # (the Pareto call)
+    eng.rollout_cost(prmd, x0, None, Kn, L, G=nS, B=Bm, want_traj=False, want_cost=True, T_total=Kn,
+                     j0_prefix=j0p, j1_prefix=j1p, w=w, seed=5, first=lo * nS)
+    torch.cuda.synchronize()
+    kt.update({k: round(v, 4) for k, v in eng.last_kernel_times().items()})
+    spot = None
+    if rank == 0:
+        o, ok = _orc(), True
+        x0h, wh = x0.cpu().numpy(), w.cpu().numpy()
+        for bb in (0, nS // 2, Bm - 1):
+            r = bb // nS
+            ub = o.random_schedule(5, lo + r, bb % nS, nS, L, Kn, np.zeros(L), reg["npi_max"]).astype(float)
+            s_, i_, al_ = o.SIalpha_Controlled(ub, *x0h[r], reg["npi_max"], 1e-8, 100.0, syn.GAMMA, reg["a"][lo + r],
+                                               reg["b"][lo + r], syn.BETA, 0.0, 0.0, 0.0, Kn, 1.0)
+            j0, j1 = o.NPICost((s_ * i_) * al_, ub, wh[r].T)
+            ok = ok and float(holder["o"]["J0"][bb]) == j0 and float(holder["o"]["J1"][bb]) == j1
+        spot = {"trajectories": 3, "bit_exact": bool(ok)}
+    front_sizes = float(full_mask[:nR].sum(dim=1).double().mean().item())
+    units = nR * nS * Kn
+    res = {"config": 5, "n_gpus": world, "scaling": "strong", "regions_this_gpu": n_loc, "schedules_per_region": nS, "days": Kn,
+           "ms_per_step": ms, "trajectory_days_per_s": units / ms * 1e3, "kernel_ms_rank0": kt,
+           "front_sizes_mean": front_sizes, "oracle_spot_check": spot,
+           "collective": "all_gather_into_tensor of the per-region front masks (uint8 [regions, schedules]) and knee indices",
+           "note": "schedules drawn in the kernel (Philox, seed 5, global counters); costs stay on the rank that made them"}
+    holder.clear()
+    del send_mask, full_mask
+    torch.cuda.empty_cache()
+    eng.release_cache()
+    return res
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)

@@ -16,3 +16,11 @@ try:
 except Exception as e:
     print("FAILED", e); print(open("gpurun_out/bench_n$N.err").read()[-1500:])
 PY
+python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_n$N.log").read().strip().splitlines()[-1])
+    print("config5_sharded", json.dumps(d.get("config5_sharded"))[:900])
+except Exception as e:
+    print("FAILED", e)
+PY
