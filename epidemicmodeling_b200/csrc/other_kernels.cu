@@ -199,11 +199,38 @@ EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (i
 
 // U_KIND: EPI_U_F64, EPI_U_U8, 2 = per-day scalars precomputed by eks_backward,
 // EPI_U_PHILOX = schedules generated in registers (no HBM stream at all)
+#ifndef EPI_PHILOX_MINB  // resident 128-thread CTAs per SM asked of the EPI_U_PHILOX instantiation (register cap)
+#define EPI_PHILOX_MINB 4
+#endif
 template <int U_KIND>
-__global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ RolloutParams P) {
+__global__ void __launch_bounds__(U_KIND == EPI_U_PHILOX ? 128 : 256, U_KIND == EPI_U_PHILOX ? EPI_PHILOX_MINB : 1)
+rollout_kernel(const __grid_constant__ RolloutParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  // EPI_U_PHILOX: the per-group constants of the day loop -- gamma*a(j), u_max(j) and the integer level range of every
+  // NPI -- as CTA tables in shared memory (a CTA spans at most two groups when G >= blockDim): read from the parameter
+  // block each day they were 24 double -> int conversions, 12 products and 48 global loads per trajectory-day
+  __shared__ double t_ga[2][EPI_LMAX], t_um[2][EPI_LMAX];
+  __shared__ unsigned t_lo[2][EPI_LMAX], t_rng[2][EPI_LMAX];
+  const long long g_cta = (P.b0 + (long long)blockIdx.x * blockDim.x) / P.G;
+  const bool tabled = (U_KIND == EPI_U_PHILOX) && P.G >= (long long)blockDim.x;
+  if (U_KIND == EPI_U_PHILOX && tabled) {
+    const long long g_last = (P.b0 + P.B - 1) / P.G;
+    if ((int)threadIdx.x < 2 * EPI_LMAX) {
+      const int gi = threadIdx.x / EPI_LMAX, j = threadIdx.x % EPI_LMAX;
+      if (j < P.L && g_cta + gi <= g_last) {
+        const epi_model_params *__restrict__ pg = P.prm + (g_cta + gi);
+        t_ga[gi][j] = pg->gamma * pg->a[j];
+        t_um[gi][j] = pg->u_max[j];
+        const int lo = (int)pg->u_min[j], hi = (int)pg->u_max[j];
+        t_lo[gi][j] = (unsigned)lo;
+        t_rng[gi][j] = (unsigned)(hi - lo + 1);
+      }
+    }
+    __syncthreads();
+  }
   if (b >= P.B) return;
   const long long g = (P.b0 + b) / P.G;
+  const int gsel = (int)(g - g_cta);  // 0 or 1 when tabled
   const epi_model_params *__restrict__ prm = P.prm + g;
   const int K = P.K, L = P.L;
   const double dt = prm->dt, beta = prm->beta, gamma = prm->gamma, bb = prm->b;
@@ -269,7 +296,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
   const unsigned rg = (unsigned)(gidx / P.G), sc = (unsigned)(gidx % P.G);
   const bool held = schedule_held((long long)sc, P.G);
   const unsigned key0 = (unsigned)P.seed, key1 = (unsigned)(P.seed >> 32);
-  unsigned lvl[EPI_LMAX];
+  double ud[(U_KIND == EPI_U_PHILOX) ? EPI_LMAX : 1], dot_keep = 0.0;  // EPI_U_PHILOX: the day's levels as doubles, its input term
   const double *__restrict__ nz = P.noise.p ? P.noise.p + P.noise.off + b : nullptr;
   // sweep: the per-day scalars of the next kRing days are kept in registers ahead of the state recursion
   constexpr int kRing = 8;
@@ -299,25 +326,48 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
     } else {
       dot = 0.0;
       const double *wd = (want_cost && P.w) ? P.w + ((size_t)g * K + t) * L : nullptr;
-      if (U_KIND == EPI_U_PHILOX && (t == 0 || !held)) {
+      if (U_KIND == EPI_U_PHILOX) {
+        // a held schedule (first half of a region's scenarios) is drawn once: its levels as doubles and its input term
+        // are kept, only the day's weighted cost is evaluated every day -- the same operations on the same operands
+        if (t == 0 || !held) {
 #pragma unroll
-        for (int q = 0; q < EPI_LMAX / 4; ++q) {
-          if (4 * q < L) {
-            const Philox4 w4 = philox4x32_10(held ? 0u : (unsigned)t, (unsigned)q, sc, rg, key0, key1);
+          for (int q = 0; q < EPI_LMAX / 4; ++q) {
+            if (4 * q < L) {
+              const Philox4 w4 = philox4x32_10(held ? 0u : (unsigned)t, (unsigned)q, sc, rg, key0, key1);
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-              if (4 * q + r < L)
-                lvl[4 * q + r] = level_from_word(w4.v[r], (int)prm->u_min[4 * q + r], (int)prm->u_max[4 * q + r]);
+              for (int r = 0; r < 4; ++r)
+                if (4 * q + r < L) {
+                  const unsigned lv = tabled ? t_lo[gsel][4 * q + r] + __umulhi(w4.v[r], t_rng[gsel][4 * q + r])
+                                             : level_from_word(w4.v[r], (int)prm->u_min[4 * q + r], (int)prm->u_max[4 * q + r]);
+                  ud[4 * q + r] = u32_to_double(lv);
+                }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < EPI_LMAX; ++j) {
+            if (j < L) {
+              const double gj = tabled ? t_ga[gsel][j] : gamma * prm->a[j];
+              const double d = (tabled ? t_um[gsel][j] : prm->u_max[j]) - ud[j];
+              dot_keep = (j == 0) ? gj * d : fma(gj, d, dot_keep);
+            }
           }
         }
-      }
+        dot = dot_keep;
+        if (wd) {
+#pragma unroll
+          for (int j = 0; j < EPI_LMAX; ++j)
+            if (j < L) {
+              const double wu = wd[j] * ud[j];
+              cday = (j == 0) ? wu : (cday + wu);
+            }
+        }
+      } else {
 #pragma unroll
       for (int j = 0; j < EPI_LMAX; ++j) {
         if (j < L) {
           double uj;
           const size_t ui = ((size_t)t * L + j) * us + (size_t)P.u_off + b;
           if (U_KIND == EPI_U_F64) uj = ((const double *)P.u)[ui];
-          else if (U_KIND == EPI_U_PHILOX) uj = u32_to_double(lvl[j]);
           else uj = (double)((const unsigned char *)P.u)[ui];
           const double gj = gamma * prm->a[j];
           const double d = prm->u_max[j] - uj;
@@ -327,6 +377,7 @@ __global__ void __launch_bounds__(256) rollout_kernel(const __grid_constant__ Ro
             cday = (j == 0) ? wu : (cday + wu);
           }
         }
+      }
       }
     }
     double n_s = 0.0, n_i = 0.0, n_a = 0.0;
