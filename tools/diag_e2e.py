@@ -8,7 +8,8 @@ from epidemicmodeling_b200 import synthetic as syn, workloads as wl
 from epidemicmodeling_b200.engine import Engine
 
 eng = Engine(0)
-inp = syn.sweep_inputs(n_regions=236, T_hist=441, T_fore=120)
+NREG = int(os.environ.get("DIAG_REGIONS", "236"))
+inp = syn.sweep_inputs(n_regions=NREG, T_hist=441, T_fore=120)
 eps = syn.epsilon_grid_xprize02(250)
 S = wl.run_fixed_input(eng, inp)
 batch = wl.sweep_batch(inp, S)
@@ -16,7 +17,7 @@ hb = dict(batch)
 for k in wl._SWEEP_ARRAYS:
     hb[k] = torch.from_numpy(np.ascontiguousarray(batch[k])).pin_memory().numpy()
 peps = torch.from_numpy(np.ascontiguousarray(eps)).pin_memory().numpy()
-nR, nE = 236, 250
+nR, nE = NREG, 250
 hout = {"J0": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
         "J1": torch.empty((nR, nE), dtype=torch.float64).pin_memory().numpy(),
         "on_front": torch.empty((nR, nE), dtype=torch.uint8).pin_memory().numpy(),
@@ -28,7 +29,7 @@ for it in range(5):
     torch.cuda.synchronize(); t0 = time.perf_counter(); dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
     print(f"raw pinned H2D 28.7 MB: {1e3*(time.perf_counter()-t0):.3f} ms", flush=True)
 print("affinity", len(os.sched_getaffinity(0)), "cpus; loadavg", os.getloadavg(), flush=True)
-for it in range(30):
+for it in range(int(os.environ.get("DIAG_ITERS", "30"))):
     t0 = time.perf_counter()
     r = wl.run_sweep(eng, hb, peps, out=hout)
     t1 = time.perf_counter()
