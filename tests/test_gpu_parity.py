@@ -1232,3 +1232,51 @@ def test_staged_backward_is_bit_identical(engine, shape, monkeypatch):
         lean = wl.run_sweep(engine, batch, eps, lean=True, **kw)
         for k in ("J0", "J1", "on_front", "I_opt", "u_fore", "u_knee"):
             assert_bits(lean[k], one[k], f"staged backward ({stages} stages) lean {k} {shape}")
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 40, 30), (3, 40, 70, 12)])
+def test_sweep_with_missing_history_npis(engine, shape, monkeypatch):
+    """NPIs missing INSIDE the history (NaN entries of u on given days): the state update replaces them by the bang-bang
+    rule (SIAlphaModelEKFOptControlled.m:41-50), so those days are evaluated per trajectory in the forward pass, the
+    gains, the backward recursion and the history cost of the rollout (no per-group shortcut).  Against the oracle on the
+    same inputs, bit for bit, under every schedule of the sweep (one stream / piped, register-prefetch / staged
+    backward, segmented forward) and in device mode."""
+    nR, nE, Th, Tf = shape
+    inp, eps = cases.sweep_case(n_regions=nR, n_eps=nE, T_hist=Th, T_fore=Tf)
+    rng = np.random.default_rng(11)
+    for rin in inp:
+        uh = np.array(rin["u_hist"], dtype=np.float64, copy=True)
+        for _ in range(6):
+            uh[rng.integers(0, uh.shape[0]), rng.integers(0, Th)] = np.nan
+        uh[:, Th // 2] = np.nan            # a day with every NPI missing
+        rin["u_hist"] = uh
+    S = wl.run_fixed_input(engine, inp)
+    batch = wl.sweep_batch(inp, S)
+    o = orc()
+    ref = []
+    for r, rin in enumerate(inp):
+        s6 = rin["setup6"]
+        reg = o.SweepRegion(s6["params"], rin["T"], Th, rin["u_hist"], rin["x"], rin["R_v"], s6["s_init"],
+                            s6["Ps_init"], s6["s_final"], s6["Ps_final"], s6["Q_w"], 1.0, 0.995, 21,
+                            batch["x0"][r, 0], batch["x0"][r, 1], batch["x0"][r, 2], batch["newcases_hist"][r],
+                            rin["weights"])
+        ref.append(o.sweep_region(reg, eps, want_u=True))
+    kw = dict(want_front=True, want_u_fore=True)
+    for env in ({}, {"EPI_PIPE": "0", "EPI_BWD_STAGES": "0"}, {"EPI_PIPE": "1", "EPI_BWD_STAGES": "3"},
+                {"EPI_PIPE": "0", "EPI_FWD_SEGMENTS": "3"}):
+        for k in ("EPI_PIPE", "EPI_BWD_STAGES", "EPI_FWD_SEGMENTS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res = wl.run_sweep(engine, batch, eps, **kw)
+        uf = res["u_fore"].reshape(Tf, 12, nR, nE)
+        for r in range(nR):
+            j0, j1, m, io, u = ref[r]
+            assert_bits(res["J0"][r], j0, f"J0 region {r} {env}")
+            assert_bits(res["J1"][r], j1, f"J1 region {r} {env}")
+            assert np.array_equal(res["on_front"][r].astype(bool), m) and res["I_opt"][r] == io
+            assert_bits(np.transpose(uf[:, :, r, :], (2, 1, 0)), u, f"u_fore region {r} {env}")
+    dbatch = wl.sweep_to_device(batch, eps, "cuda:0")
+    dres = wl.run_sweep(engine, dbatch, None, want_front=True)
+    assert_bits(dres["J0"].cpu().numpy(), res["J0"], "device mode J0")
+    assert_bits(dres["J1"].cpu().numpy(), res["J1"], "device mode J1")
