@@ -1280,3 +1280,39 @@ def test_sweep_with_missing_history_npis(engine, shape, monkeypatch):
     dres = wl.run_sweep(engine, dbatch, None, want_front=True)
     assert_bits(dres["J0"].cpu().numpy(), res["J0"], "device mode J0")
     assert_bits(dres["J1"].cpu().numpy(), res["J1"], "device mode J1")
+
+
+def test_pareto_pruned_path_special_values(engine):
+    """Large point sets are pruned by J0 buckets before the sort (csrc/pareto_sorted.cu): the mask must stay the O(n^2)
+    predicate's for ties, NaN / +-Inf / +-0 in either coordinate, a degenerate J0 range (every point in one bucket), an
+    overflowing range, negative costs and a set whose front is everything."""
+    rng = np.random.default_rng(21)
+    n = 9500
+    o = orc()
+    sets0, sets1 = [], []
+    a0, a1 = np.round(rng.random(n), 2), np.round(rng.random(n), 2)                     # heavy ties
+    a0[:7] = [np.nan, np.inf, -np.inf, 0.0, -0.0, np.inf, np.nan]
+    a1[3:12] = [np.nan, 0.0, -0.0, np.inf, -np.inf, np.nan, 5.0, -5.0, 0.5]
+    sets0.append(a0); sets1.append(a1)
+    sets0.append(np.full(n, 3.25)); sets1.append(rng.random(n))                           # degenerate range
+    b0 = rng.standard_normal(n) * 1e307; b0[0], b0[1] = 1.7e308, -1.7e308                 # hi - lo overflows
+    sets0.append(b0); sets1.append(rng.standard_normal(n))
+    c0 = np.sort(rng.random(n)); sets0.append(c0); sets1.append(1.0 - c0)                 # everything on the front
+    sets0.append(-rng.random(n) * 1e-300); sets1.append(-rng.random(n))                   # tiny negative J0, negative J1
+    J0, J1 = np.stack(sets0), np.stack(sets1)
+    m, io = engine.pareto(J0, J1)
+    for r in range(J0.shape[0]):
+        wm, wi = o.pareto(J0[r], J1[r])
+        assert np.array_equal(m[r].astype(bool), wm), ("pruned path mask", r, int(m[r].sum()), int(wm.sum()))
+        assert io[r] == wi, ("knee", r)
+    # a realistic cloud at config 5's size: idempotence and front size
+    J0b = rng.random((2, 100_000)); J1b = 1.0 / (J0b + 0.05) + 0.1 * rng.random((2, 100_000))
+    mb, _ = engine.pareto(J0b, J1b)
+    for r in range(2):
+        keep = mb[r].astype(bool)
+        wm, _ = o.pareto(J0b[r, keep], J1b[r, keep])
+        assert wm.all() and 10 < keep.sum() < 5000
+        # no dropped front point: every point is dominated by some kept point or kept itself (checked on a sample)
+        k0, k1 = J0b[r, keep], J1b[r, keep]
+        for i in rng.integers(0, 100_000, 300):
+            assert keep[i] or np.any((k0 < J0b[r, i]) & (k1 < J1b[r, i]))
