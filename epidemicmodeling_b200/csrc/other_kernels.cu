@@ -202,7 +202,9 @@ EPI_DI double u32_to_double(unsigned v) { return __hiloint2double(0x43300000, (i
 #ifndef EPI_PHILOX_MINB  // resident 128-thread CTAs per SM asked of the EPI_U_PHILOX instantiation (register cap)
 #define EPI_PHILOX_MINB 4
 #endif
-template <int U_KIND>
+// LC: compile-time number of NPIs (12, the OxCGRT shape) or 0 = run-time P.L -- the twelve-fold loops of the day are
+// then straight-line code (the run-time bound cost ~26 branches and compares per trajectory-day, ncu)
+template <int U_KIND, int LC = 0>
 __global__ void __launch_bounds__(U_KIND == EPI_U_PHILOX ? 128 : 256, U_KIND == EPI_U_PHILOX ? EPI_PHILOX_MINB : 1)
 rollout_kernel(const __grid_constant__ RolloutParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -232,7 +234,7 @@ rollout_kernel(const __grid_constant__ RolloutParams P) {
   const long long g = (P.b0 + b) / P.G;
   const int gsel = (int)(g - g_cta);  // 0 or 1 when tabled
   const epi_model_params *__restrict__ prm = P.prm + g;
-  const int K = P.K, L = P.L;
+  const int K = P.K, L = LC ? LC : P.L;
   const double dt = prm->dt, beta = prm->beta, gamma = prm->gamma, bb = prm->b;
   const double amin = prm->alpha_min, amax = prm->alpha_max;
   double S = P.x0[3 * g + 0], I = P.x0[3 * g + 1], A = P.x0[3 * g + 2];
@@ -680,6 +682,7 @@ void launch_rollout(const RolloutParams &p, cudaStream_t st) {
   const int grid = (p.B + block - 1) / block;
   if (p.u_kind == EPI_U_F64) rollout_kernel<EPI_U_F64><<<grid, block, 0, st>>>(p);
   else if (p.u_kind == EPI_U_U8) rollout_kernel<EPI_U_U8><<<grid, block, 0, st>>>(p);
+  else if (p.u_kind == EPI_U_PHILOX && p.L == 12) rollout_kernel<EPI_U_PHILOX, 12><<<grid, block, 0, st>>>(p);
   else if (p.u_kind == EPI_U_PHILOX) rollout_kernel<EPI_U_PHILOX><<<grid, block, 0, st>>>(p);
   else rollout_kernel<2><<<grid, block, 0, st>>>(p);
 }
