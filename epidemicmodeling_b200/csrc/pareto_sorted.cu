@@ -13,8 +13,8 @@
 // scatter kernels are ours.
 //
 // Pruning before the sort (round 2): of 100 000 random schedules ~3 % are on the front, and sorting whole 100k-point
-// segments took 1.6 of the step's 2.6 ms (30 sets).  The J0 range of a set is cut into kBuckets equal buckets (a
-// monotone map: a point in a LOWER bucket has a STRICTLY smaller J0), every bucket keeps its minimum J1, and a point
+// segments took 1.6 of the step's 2.6 ms (30 sets).  The J0 range of a set is cut into kBuckets buckets (a monotone
+// map, see bucket_of: a point in a LOWER bucket has a STRICTLY smaller J0), every bucket keeps its minimum J1, and a point
 // whose J1 exceeds the minimum over all lower buckets is dominated for certain.  Only the survivors are sorted and
 // tested exactly; a survivor can only be dominated by another survivor (if y dominates x and z, from a lower bucket
 // than y, dominates y, then z prunes x as well), so the mask is the reference's, bit for bit.
@@ -47,7 +47,7 @@ constexpr int kPruneChunk = 8192;  // points of one set per CTA
 
 // order-preserving map double -> uint64 (for atomicMin / atomicMax); NaN is never passed in
 __device__ __forceinline__ unsigned long long ord64(double v) {
-  const long long b = __double_as_longlong(v);
+  const long long b = __double_as_longlong(v + 0.0);  // -0 and +0 compare equal: one pattern for both
   return (b < 0) ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
 }
 __device__ __forceinline__ double ord64_inv(unsigned long long u) {
@@ -63,12 +63,20 @@ struct PruneBufs {
   int *seg_begin, *seg_end;   // [n_sets]: the survivors of set s live at s*n + [0, count)
 };
 
-// bucket of a point: monotone non-decreasing in x0 (-inf -> 0, +inf -> last)
-__device__ __forceinline__ int bucket_of(double x0, double lo, double scale) {
-  if (x0 == __longlong_as_double(0x7ff0000000000000ll)) return kBuckets - 1;
-  const double t = (x0 - lo) * scale;  // (NaN from inf * 0 converts to 0)
-  int b = (t >= (double)(kBuckets - 1)) ? kBuckets - 1 : (int)t;
-  return b < 0 ? 0 : b;
+// Bucket of a point: monotone non-decreasing in x0.  The buckets are equal steps of the ORDER-PRESERVING BIT PATTERN of
+// J0 between the set's finite minimum and maximum, i.e. logarithmic in the value: the infection cost of random schedules
+// spans five decades, and equal-width buckets left 15 % of the points (83 % in the worst region) to the sort where
+// these leave 2.9 % -- the front itself is 2.8 % (measured on config 5's costs, 30 regions x 100 000 schedules).
+struct BucketMap {
+  unsigned long long lo;  // ordered bit pattern of the smallest finite J0
+  int shift;              // (ord - lo) >> shift < 2^20
+  double inv;             // kBuckets / (((hi - lo) >> shift) + 1)
+};
+__device__ __forceinline__ int bucket_of(double x0, const BucketMap &m) {
+  const unsigned long long o = ord64(x0);
+  if (o <= m.lo) return 0;
+  const double t = (double)((o - m.lo) >> m.shift) * m.inv;
+  return (t >= (double)(kBuckets - 1)) ? kBuckets - 1 : (int)t;
 }
 
 __global__ void prune_init_kernel(PruneBufs B, int n_sets, int n) {
@@ -100,16 +108,18 @@ __global__ void __launch_bounds__(kPruneBlock) prune_range_kernel(const double *
   }
 }
 
-// lo and scale of a set's bucket map (scale = 0: everything in bucket 0, nothing is pruned)
-__device__ __forceinline__ void bucket_map(const PruneBufs &B, int set, double &lo, double &scale) {
+// the bucket map of a set (no finite J0: everything lands in bucket 0 or the last one, nothing is pruned wrongly)
+__device__ __forceinline__ BucketMap bucket_map(const PruneBufs &B, int set) {
   const unsigned long long l = B.range[2 * set], h = B.range[2 * set + 1];
-  lo = 0.0; scale = 0.0;
+  BucketMap m;
+  m.lo = l; m.shift = 0; m.inv = (double)kBuckets;
   if (l <= h && l != ~0ull) {
-    lo = ord64_inv(l);
-    const double w = ord64_inv(h) - lo;
-    if (w > 0.0 && finite64(w)) scale = (double)kBuckets / w;
-    if (!finite64(scale)) scale = 0.0;
+    const unsigned long long range = h - l;
+    const int bits = 64 - __clzll((long long)range);  // 0 for range == 0
+    m.shift = bits > 20 ? bits - 20 : 0;
+    m.inv = (double)kBuckets / ((double)(range >> m.shift) + 1.0);
   }
+  return m;
 }
 
 __global__ void __launch_bounds__(kPruneBlock) prune_bucket_kernel(const double *__restrict__ J0,
@@ -118,12 +128,11 @@ __global__ void __launch_bounds__(kPruneBlock) prune_bucket_kernel(const double 
   const int set = blockIdx.y, base = blockIdx.x * kPruneChunk;
   for (int b = threadIdx.x; b < kBuckets; b += kPruneBlock) sm[b] = ~0ull;
   __syncthreads();
-  double lo, scale;
-  bucket_map(B, set, lo, scale);
+  const BucketMap bm = bucket_map(B, set);
   const double *j0 = J0 + (size_t)set * n, *j1 = J1 + (size_t)set * n;
   for (int i = base + threadIdx.x; i < n && i < base + kPruneChunk; i += kPruneBlock) {
     const double x0 = j0[i], x1 = j1[i];
-    if (x0 == x0 && x1 == x1) atomicMin(&sm[bucket_of(x0, lo, scale)], ord64(x1));  // a NaN never dominates
+    if (x0 == x0 && x1 == x1) atomicMin(&sm[bucket_of(x0, bm)], ord64(x1));  // a NaN never dominates
   }
   __syncthreads();
   for (int b = threadIdx.x; b < kBuckets; b += kPruneBlock)
@@ -148,8 +157,7 @@ __global__ void __launch_bounds__(kPruneBlock) prune_compact_kernel(const double
                                                                      const double *__restrict__ J1, int n, PruneBufs B,
                                                                      double *__restrict__ keys, int *__restrict__ idx) {
   const int set = blockIdx.y, base = blockIdx.x * kPruneChunk;
-  double lo, scale;
-  bucket_map(B, set, lo, scale);
+  const BucketMap bm = bucket_map(B, set);
   const double *j0 = J0 + (size_t)set * n, *j1 = J1 + (size_t)set * n;
   const double *pm = B.pmin + (size_t)set * kBuckets;
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(kPruneBlock) prune_compact_kernel(const double
     if (i < n && i < base + kPruneChunk) {
       x0 = j0[i];
       const double x1 = j1[i];
-      keep = !(x0 == x0) || !(pm[bucket_of(x0, lo, scale)] < x1);   // NaN J0 is never dominated; NaN J1 compares false
+      keep = !(x0 == x0) || !(pm[bucket_of(x0, bm)] < x1);   // NaN J0 is never dominated; NaN J1 compares false
     }
     // warp-aggregated append
     const unsigned m = __ballot_sync(0xffffffffu, keep);

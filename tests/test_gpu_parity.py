@@ -1299,6 +1299,10 @@ def test_pareto_pruned_path_special_values(engine):
     sets0.append(b0); sets1.append(rng.standard_normal(n))
     c0 = np.sort(rng.random(n)); sets0.append(c0); sets1.append(1.0 - c0)                 # everything on the front
     sets0.append(-rng.random(n) * 1e-300); sets1.append(-rng.random(n))                   # tiny negative J0, negative J1
+    d0 = np.round(10.0 ** rng.uniform(-300, 300, n), 0) * rng.choice([-1.0, 1.0], n)     # 600 decades, both signs, ties at 0
+    d0[:6] = [5e-324, -5e-324, 0.0, -0.0, 2.2250738585072014e-308, -2.2250738585072014e-308]
+    sets0.append(d0); sets1.append(np.round(rng.standard_normal(n), 1))
+    e0 = 10.0 ** rng.uniform(-8, -2, n); sets0.append(e0); sets1.append(3.0 * rng.random(n) ** 2 + 1e-3 / e0 ** 0.25)  # config-5-like
     J0, J1 = np.stack(sets0), np.stack(sets1)
     m, io = engine.pareto(J0, J1)
     for r in range(J0.shape[0]):
