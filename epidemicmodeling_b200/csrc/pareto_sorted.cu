@@ -330,8 +330,8 @@ int launch_pareto_sorted(const ParetoParams &p, void *scratch, size_t scratch_by
     B.seg_end = (int *)w; w += (size_t)p.n_sets * 4;
     w = (char *)(((size_t)w + 255) & ~(size_t)255);  // cub temp storage: 256-byte aligned
     size_t cub_bytes = scratch_bytes - (size_t)(w - (char *)scratch);
-    static int prune = -1;
-    if (prune < 0) { const char *e = getenv("EPI_PARETO_PRUNE"); prune = e ? atoi(e) : 1; }
+    int prune = 1;
+    if (const char *e = getenv("EPI_PARETO_PRUNE")) prune = atoi(e);  // 0: sort whole sets (the parity tests compare both)
     if (prune) {
       const dim3 grid((unsigned)((p.n + kPruneChunk - 1) / kPruneChunk), (unsigned)p.n_sets);
       const size_t ninit = (size_t)p.n_sets * kBuckets;

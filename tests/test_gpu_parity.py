@@ -1309,6 +1309,12 @@ def test_pareto_pruned_path_special_values(engine):
         wm, wi = o.pareto(J0[r], J1[r])
         assert np.array_equal(m[r].astype(bool), wm), ("pruned path mask", r, int(m[r].sum()), int(wm.sum()))
         assert io[r] == wi, ("knee", r)
+    os.environ["EPI_PARETO_PRUNE"] = "0"        # the whole-set sort must agree as well
+    try:
+        m0, io0 = engine.pareto(J0, J1)
+    finally:
+        del os.environ["EPI_PARETO_PRUNE"]
+    assert np.array_equal(m0, m) and np.array_equal(io0, io)
     # a realistic cloud at config 5's size: idempotence and front size
     J0b = rng.random((2, 100_000)); J1b = 1.0 / (J0b + 0.05) + 0.1 * rng.random((2, 100_000))
     mb, _ = engine.pareto(J0b, J1b)
