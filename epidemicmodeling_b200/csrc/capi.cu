@@ -1162,6 +1162,7 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
     const long long Bw = plan_wave(c, B, per);
     tr.mark("budget");
 
+    double *hist_pre0 = nullptr, *hist_pre1 = nullptr;  // per-region NPICost sums over the history (launch_hist_prefix)
     for (long long b0 = 0; b0 < B; b0 += Bw) {
       const long long nb = (B - b0 < Bw) ? (B - b0) : Bw;
       Call w(c, a->mem);
@@ -1279,6 +1280,13 @@ extern "C" int epi_sweep(epi_ctx *c, const epi_sweep_args *a) {
       // group (L1) instead of 441 per-trajectory tape lines; days with missing NPIs keep the per-trajectory value
       r.hist_cost_grp = cost_grp;
       r.hist_cost_per_traj = a->lean ? 0 : 1;
+      if (!hist_pre0) {  // once per call, when the per-group day costs are complete (the weights may have arrived late)
+        hist_pre0 = (double *)shared.dalloc((size_t)nR * 8);
+        hist_pre1 = (double *)shared.dalloc((size_t)nR * 8);
+        launch_hist_prefix(nch, cost_grp, (int)nR, a->T_hist, T, hist_pre0, hist_pre1, c->stream);
+        check_launch(c, 1);
+      }
+      r.j0_prefix = hist_pre0; r.j1_prefix = hist_pre1;
       r.B = (int)nb; r.K = Tf; r.L = L; r.G = a->n_eps; r.b0 = b0;
       r.prm = prm; r.x0 = x0; r.noise_std = nstd;
       r.u_kind = 2;

@@ -127,6 +127,10 @@ struct RolloutParams {
   TArr J0, J1;                    // [B]
 };
 void launch_rollout(const RolloutParams &p, cudaStream_t st);
+// sweep: the NPICost sums over the (given) history are the same for every trajectory of a region: one thread per region
+// adds them in day order; pre1[g] = NaN marks a region whose history has a day with missing NPIs (per-trajectory sums)
+void launch_hist_prefix(const double *newcases_hist, const double *cost_grp, int n_groups, int T_hist, int T_total,
+                        double *pre0, double *pre1, cudaStream_t st);
 // write the EPI_U_PHILOX schedules: u [K][L][stride] uint8, trajectories first + b0 + (0..B-1)
 void launch_random_schedules(const epi_model_params *prm, unsigned long long seed, long long first, int B, int K,
                              int L, int G, unsigned char *u, long long stride, long long off, cudaStream_t st);
