@@ -197,3 +197,26 @@ def gather_costs(J0, J1, group=None):
     g0 = torch.cat([recv[r, 0, :sizes[r]] for r in range(ws)])
     g1 = torch.cat([recv[r, 1, :sizes[r]] for r in range(ws)])
     return g0, g1
+
+
+def gather_fronts(on_front, I_opt, group=None):
+    """Config 5 at N GPUs (TrainPredictPrescribeNPI.m:500-521 + :624-633 per region): every rank scores the random
+    schedules of ITS regions and extracts their Pareto fronts; this is the path's one collective -- all-gather of the
+    per-region front masks (uint8 [n_local_regions, n_schedules]) and knee indices (int32 [n_local_regions]).
+    Ragged shards (last rank) are padded to the largest shard; returns the masks and knees of all regions in order."""
+    import torch.distributed as dist
+    ws = dist.get_world_size(group)
+    n_loc, nS = int(on_front.shape[0]), int(on_front.shape[1])
+    sizes = [torch.zeros(1, dtype=torch.int64, device=on_front.device) for _ in range(ws)]
+    dist.all_gather(sizes, torch.tensor([n_loc], dtype=torch.int64, device=on_front.device), group=group)
+    sizes = [int(s.item()) for s in sizes]
+    mx = max(sizes)
+    send_m = torch.zeros((mx, nS), dtype=torch.uint8, device=on_front.device)
+    send_i = torch.zeros((mx,), dtype=torch.int32, device=on_front.device)
+    send_m[:n_loc] = on_front
+    send_i[:n_loc] = I_opt
+    recv_m = torch.empty((ws, mx, nS), dtype=torch.uint8, device=on_front.device)
+    recv_i = torch.empty((ws, mx), dtype=torch.int32, device=on_front.device)
+    dist.all_gather_into_tensor(recv_m.view(-1), send_m.view(-1), group=group)
+    dist.all_gather_into_tensor(recv_i.view(-1), send_i.view(-1), group=group)
+    return (torch.cat([recv_m[r, :sizes[r]] for r in range(ws)]), torch.cat([recv_i[r, :sizes[r]] for r in range(ws)]))

@@ -192,6 +192,62 @@ def test_gather_costs_world_size_2_gloo(tmp_path):
         assert p.returncode == 0, o
 
 
+
+_GLOO_C5_SCRIPT = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import numpy as np, torch, torch.distributed as dist
+    from oracle import oracle as orc            # stand-in compute for the CPU test (no GPU here)
+    from epidemicmodeling_b200 import synthetic as syn
+    from epidemicmodeling_b200.workloads import shard_regions, gather_fronts
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+    rank = dist.get_rank()
+    nR, nS, Kn, L, seed = 3, 14, 9, 12, 5         # ragged: 2 + 1 regions
+    reg = syn.load_regions(nR)
+
+    def score(regions):
+        # the schedules are a function of the GLOBAL (region, scenario) pair: a shard draws exactly what the whole job draws
+        masks, knees = [], []
+        for r in regions:
+            J0, J1 = np.zeros(nS), np.zeros(nS)
+            for sc in range(nS):
+                u = orc.random_schedule(seed, r, sc, nS, L, Kn, np.zeros(L), reg["npi_max"]).astype(float)
+                s_, i_, al_ = orc.SIalpha_Controlled(u, (reg["N"][r] - 10) / reg["N"][r], 10 / reg["N"][r], syn.ALPHA0,
+                                                     reg["npi_max"], 1e-8, 100.0, syn.GAMMA, reg["a"][r], reg["b"][r], syn.BETA,
+                                                     0.0, 0.0, 0.0, Kn, 1.0)
+                J0[sc], J1[sc] = orc.NPICost((s_ * i_) * al_, u, np.repeat(reg["cost_weights"][r][:, None], Kn, axis=1))
+            m, k = orc.pareto(J0, J1)
+            masks.append(m.astype(np.uint8)); knees.append(k)
+        return torch.from_numpy(np.array(masks, dtype=np.uint8).reshape(len(regions), nS)), torch.tensor(knees, dtype=torch.int32)
+
+    lo, hi = shard_regions(nR, 2, rank)
+    m_loc, k_loc = score(range(lo, hi))
+    m_all, k_all = gather_fronts(m_loc, k_loc)
+    m_ref, k_ref = score(range(nR))               # the unsharded answer
+    assert torch.equal(m_all, m_ref) and torch.equal(k_all, k_ref), rank
+    dist.barrier(); dist.destroy_process_group()
+    print("ok", rank)
+""")
+
+
+def test_config5_front_gather_world_size_2_gloo(tmp_path):
+    """BASELINE config 5 at N > 1 (bench.py `config5_sharded`): regions sharded over the ranks, schedules drawn from
+    global counters, per-region Pareto on the owning rank, ONE all-gather of front masks and knees -- equal to the
+    unsharded job (oracle as the stand-in compute on the CPU)."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "gloo_c5.py"
+    script.write_text(_GLOO_C5_SCRIPT.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
 def test_mex_gateway_type_checks_against_stub_header():
     """matlab/epi_mex.cpp cannot be built here (no MATLAB/Octave); at least prove it is well-formed C++
     against the documented MEX API subset (tests/stubs/mex.h) and the real C-ABI header."""
